@@ -1,0 +1,3 @@
+"""ecfft_b200 — B200-native ECFFT engine behind the reference crate's FFTree<secp256k1::Fp> surface."""
+from ._lib import EcfftError, LIB_PATH  # noqa: F401
+from .fftree import FFTree, Moiety, build_fftree, PARTS_FULL, PARTS_ENTER_ONLY  # noqa: F401

@@ -1,0 +1,97 @@
+"""ctypes loader for ecfft_b200/lib/libecfft_b200.so (the C ABI declared in include/ecfft_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing, or a call needs a GPU that is not
+there, the failure is loud (ImportError / EcfftError).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libecfft_b200.so")
+
+ECFFT_OK = 0
+ERR_NOT_POW2 = 1
+ERR_TREE_TOO_SMALL = 2
+ERR_BAD_BYTES = 3
+ERR_CUDA = 4
+ERR_INVALID_ARG = 5
+ERR_TOO_LARGE = 6
+ERR_MISSING_TABLES = 7
+ERR_BUFFER_TOO_SMALL = 8
+
+# every symbol include/ecfft_b200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    "ecfft_last_error", "ecfft_device_count",
+    "ecfft_tree_build_secp256k1", "ecfft_tree_new", "ecfft_tree_deserialize",
+    "ecfft_tree_serialized_size", "ecfft_tree_serialize", "ecfft_tree_free",
+    "ecfft_tree_leaves", "ecfft_tree_device", "ecfft_tree_table",
+    "ecfft_enter", "ecfft_exit", "ecfft_extend", "ecfft_mextend", "ecfft_degree",
+    "ecfft_redc_z0", "ecfft_redc_z1", "ecfft_modular_reduce", "ecfft_vanish",
+    "ecfft_enter_dev", "ecfft_exit_dev", "ecfft_extend_dev", "ecfft_mextend_dev",
+    "ecfft_degree_dev", "ecfft_redc_z0_dev", "ecfft_redc_z1_dev",
+    "ecfft_modular_reduce_dev", "ecfft_vanish_dev", "ecfft_enter_range_dev",
+]
+
+
+class EcfftError(RuntimeError):
+    """Raised where the reference would panic or return a SerializationError."""
+
+    def __init__(self, code, message):
+        super().__init__(f"ecfft_b200 error {code}: {message}")
+        self.code = code
+
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C ecfft_b200/csrc`). ecfft_b200 has no CPU fallback.")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, sz, ci = ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int
+    psz, pvp = ctypes.POINTER(ctypes.c_size_t), ctypes.POINTER(ctypes.c_void_p)
+    L.ecfft_last_error.restype = ctypes.c_char_p
+    L.ecfft_last_error.argtypes = []
+    L.ecfft_device_count.argtypes = [ctypes.POINTER(ci)]
+    L.ecfft_tree_build_secp256k1.argtypes = [sz, ci, ci, pvp]
+    L.ecfft_tree_new.argtypes = [vp, sz, vp, vp, sz, ci, ci, pvp]
+    L.ecfft_tree_deserialize.argtypes = [vp, sz, ci, ci, pvp]
+    L.ecfft_tree_serialized_size.argtypes = [vp, ci, psz]
+    L.ecfft_tree_serialize.argtypes = [vp, ci, vp, sz, psz]
+    L.ecfft_tree_free.argtypes = [vp]
+    L.ecfft_tree_free.restype = None
+    L.ecfft_tree_leaves.argtypes = [vp]
+    L.ecfft_tree_leaves.restype = sz
+    L.ecfft_tree_device.argtypes = [vp]
+    L.ecfft_tree_table.argtypes = [vp, sz, ctypes.c_char_p, vp, sz, psz]
+    for name in ("ecfft_enter", "ecfft_exit"):
+        getattr(L, name).argtypes = [vp, vp, sz, vp]
+    for name in ("ecfft_extend", "ecfft_mextend"):
+        getattr(L, name).argtypes = [vp, vp, sz, ci, vp]
+    L.ecfft_degree.argtypes = [vp, vp, sz, psz]
+    for name in ("ecfft_redc_z0", "ecfft_redc_z1"):
+        getattr(L, name).argtypes = [vp, vp, vp, sz, vp]
+    L.ecfft_modular_reduce.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.ecfft_vanish.argtypes = [vp, vp, sz, vp]
+    for name in ("ecfft_enter_dev", "ecfft_exit_dev"):
+        getattr(L, name).argtypes = [vp, vp, sz, vp, vp]
+    for name in ("ecfft_extend_dev", "ecfft_mextend_dev"):
+        getattr(L, name).argtypes = [vp, vp, sz, ci, vp, vp]
+    L.ecfft_degree_dev.argtypes = [vp, vp, sz, psz, vp]
+    for name in ("ecfft_redc_z0_dev", "ecfft_redc_z1_dev"):
+        getattr(L, name).argtypes = [vp, vp, vp, sz, vp, vp]
+    L.ecfft_modular_reduce_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp]
+    L.ecfft_vanish_dev.argtypes = [vp, vp, sz, vp, vp]
+    L.ecfft_enter_range_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+    _lib = L
+    return L
+
+
+def check(rc):
+    if rc != ECFFT_OK:
+        raise EcfftError(rc, load().ecfft_last_error().decode(errors="replace"))

@@ -1,0 +1,371 @@
+// extern "C" boundary (include/ecfft_b200.h).  Maps engine exceptions to status codes and moves
+// host buffers through the handle's stream.  No torch types, no CPU fallback: every entry point
+// that computes needs a CUDA device and fails with ECFFT_ERR_CUDA without one.
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/ecfft_b200.h"
+#include "engine.h"
+
+using namespace ecfft;
+
+struct ecfft_tree {
+  Tree* tree;
+  std::mutex mu;  // host-buffer calls share the handle's stream and are serialised
+};
+
+static thread_local std::string g_last_error;
+
+template <class F>
+static int guard(F f) {
+  try {
+    f();
+    return ECFFT_OK;
+  } catch (const Error& e) {
+    g_last_error = e.what();
+    return e.code;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return ECFFT_ERR_INVALID_ARG;
+  }
+}
+static void require(bool ok, int code, const char* msg) {
+  if (!ok) throw Error(code, msg);
+}
+static const Fp* dptr(const void* p) {
+  require(p != nullptr && ((uintptr_t)p & 15) == 0, ERR_INVALID_ARG, "device pointer must be non-null and 16-byte aligned");
+  return (const Fp*)p;
+}
+static Fp* dptr(void* p) { return (Fp*)dptr((const void*)p); }
+static cudaStream_t pick_stream(const ecfft_tree* t, void* stream) { return stream ? (cudaStream_t)stream : t->tree->stream; }
+
+namespace {
+// scoped device buffer fed from / drained to host memory on the handle's stream
+struct HostIO {
+  const Tree& t;
+  cudaStream_t st;
+  std::vector<void*> bufs;
+  HostIO(const Tree& tree) : t(tree), st(tree.stream) { ECFFT_CUDA(cudaSetDevice(tree.device)); }
+  ~HostIO() {
+    for (void* b : bufs) cudaFreeAsync(b, st);
+    cudaStreamSynchronize(st);
+  }
+  Fp* alloc(size_t count) {
+    void* p = nullptr;
+    ECFFT_CUDA(cudaMallocAsync(&p, (count ? count : 1) * sizeof(Fp), st));
+    bufs.push_back(p);
+    return (Fp*)p;
+  }
+  Fp* in(const uint64_t* host, size_t count) {
+    require(host != nullptr || count == 0, ERR_INVALID_ARG, "null input buffer");
+    Fp* d = alloc(count);
+    if (count) ECFFT_CUDA(cudaMemcpyAsync(d, host, count * sizeof(Fp), cudaMemcpyHostToDevice, st));
+    return d;
+  }
+  void out(uint64_t* host, const Fp* d, size_t count) {
+    require(host != nullptr || count == 0, ERR_INVALID_ARG, "null output buffer");
+    if (count) ECFFT_CUDA(cudaMemcpyAsync(host, d, count * sizeof(Fp), cudaMemcpyDeviceToHost, st));
+    ECFFT_CUDA(cudaStreamSynchronize(st));
+  }
+};
+}  // namespace
+
+extern "C" {
+
+const char* ecfft_last_error(void) { return g_last_error.c_str(); }
+
+int ecfft_device_count(int* count) {
+  return guard([&] {
+    require(count != nullptr, ERR_INVALID_ARG, "null count");
+    ECFFT_CUDA(cudaGetDeviceCount(count));
+  });
+}
+
+int ecfft_tree_build_secp256k1(size_t n, int parts, int device, ecfft_tree** out) {
+  return guard([&] {
+    require(out != nullptr, ERR_INVALID_ARG, "null out");
+    require(parts == PARTS_FULL || parts == PARTS_ENTER_ONLY, ERR_INVALID_ARG, "bad parts");
+    ecfft_tree* h = new ecfft_tree();
+    try {
+      h->tree = build_secp256k1(n, parts, device);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    *out = h;
+  });
+}
+
+int ecfft_tree_new(const uint64_t* leaves, size_t n, const uint64_t* map_coeffs, const size_t* map_lens, size_t nmaps,
+                   int parts, int device, ecfft_tree** out) {
+  return guard([&] {
+    require(out && leaves && (nmaps == 0 || (map_coeffs && map_lens)), ERR_INVALID_ARG, "null argument");
+    require(n && !(n & (n - 1)), ERR_NOT_POW2, "leaf count is not a power of two");
+    ECFFT_CUDA(cudaSetDevice(device));
+    // Montgomery -> plain: leaves on the device, the few map coefficients on the host
+    std::vector<RatMapHost> maps(nmaps);
+    const Fp rinv = fp_const_RINV();
+    size_t off = 0;
+    for (size_t i = 0; i < nmaps; i++)
+      for (int part = 0; part < 2; part++) {
+        size_t cnt = map_lens[2 * i + part];
+        std::vector<Fp>& dst = part == 0 ? maps[i].num : maps[i].den;
+        dst.resize(cnt);
+        for (size_t c = 0; c < cnt; c++) {
+          Fp x;
+          memcpy(&x, map_coeffs + 4 * (off + c), sizeof(Fp));
+          dst[c] = fp_mul(x, rinv);
+        }
+        off += cnt;
+      }
+    Fp* d = nullptr;
+    ECFFT_CUDA(cudaMalloc((void**)&d, n * sizeof(Fp)));
+    ecfft_tree* h = new ecfft_tree();
+    try {
+      ECFFT_CUDA(cudaMemcpy(d, leaves, n * sizeof(Fp), cudaMemcpyHostToDevice));
+      k::mul_const(d, d, rinv, n, nullptr);
+      ECFFT_CUDA(cudaDeviceSynchronize());
+      h->tree = tree_from_leaves(d, n, maps, parts, device);
+    } catch (...) {
+      cudaFree(d);
+      delete h;
+      throw;
+    }
+    cudaFree(d);
+    *out = h;
+  });
+}
+
+int ecfft_tree_deserialize(const uint8_t* bytes, size_t len, int compressed, int device, ecfft_tree** out) {
+  return guard([&] {
+    require(out && bytes, ERR_INVALID_ARG, "null argument");
+    ecfft_tree* h = new ecfft_tree();
+    try {
+      h->tree = deserialize(bytes, len, compressed != 0, device);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    *out = h;
+  });
+}
+
+int ecfft_tree_serialized_size(const ecfft_tree* t, int compressed, size_t* size) {
+  return guard([&] {
+    require(t && size, ERR_INVALID_ARG, "null argument");
+    *size = serialized_size(*t->tree, compressed != 0);
+  });
+}
+
+int ecfft_tree_serialize(const ecfft_tree* t, int compressed, uint8_t* buf, size_t cap, size_t* written) {
+  return guard([&] {
+    require(t && buf && written, ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(const_cast<ecfft_tree*>(t)->mu);
+    ECFFT_CUDA(cudaSetDevice(t->tree->device));
+    *written = serialize(*t->tree, compressed != 0, buf, cap);
+  });
+}
+
+void ecfft_tree_free(ecfft_tree* t) {
+  if (!t) return;
+  delete t->tree;
+  delete t;
+}
+
+size_t ecfft_tree_leaves(const ecfft_tree* t) { return t ? t->tree->n() : 0; }
+int ecfft_tree_device(const ecfft_tree* t) { return t ? t->tree->device : -1; }
+
+int ecfft_tree_table(const ecfft_tree* t, size_t subtree_leaves, const char* name, uint64_t* out, size_t cap_elems, size_t* count) {
+  return guard([&] {
+    require(t && name && count, ERR_INVALID_ARG, "null argument");
+    std::lock_guard<std::mutex> lock(const_cast<ecfft_tree*>(t)->mu);
+    const Tree& tr = *t->tree;
+    HostIO io(tr);
+    Engine eng(tr, io.st);
+    const Level& lv = eng.level_for(subtree_leaves);
+    const size_t N = subtree_leaves, h = N / 2, n = tr.n();
+    const Fp* src = nullptr;
+    size_t cnt = 0;
+    Fp* staged = nullptr;
+    std::string nm(name);
+    if (nm == "f") {
+      cnt = 2 * N;
+      if (out) {
+        staged = io.alloc(cnt);
+        ECFFT_CUDA(cudaMemsetAsync(staged, 0, sizeof(Fp), io.st));
+        for (uint32_t kk = 0; kk <= lv.log_n; kk++) k::copy_strided(staged + (N >> kk), tr.f + (n >> kk), N >> kk, n / N, io.st);
+        src = staged;
+      }
+    } else if (nm == "recombine_matrices") { src = lv.rmat; cnt = 4 * N; }
+    else if (nm == "decompose_matrices") { src = lv.dmat; cnt = 4 * N; }
+    else if (nm == "xnn_s") { src = lv.xnn_s; cnt = N; }
+    else if (nm == "xnn_s_inv") { src = lv.xnn_s_inv; cnt = N; }
+    else if (nm == "z0_s1") { src = lv.z0_s1; cnt = h; }
+    else if (nm == "z1_s0") { src = lv.z1_s0; cnt = h; }
+    else if (nm == "z0_inv_s1") { src = lv.z0_inv_s1; cnt = h; }
+    else if (nm == "z1_inv_s0") { src = lv.z1_inv_s0; cnt = h; }
+    else if (nm == "z0z0_rem_xnn_s") { src = lv.z0z0; cnt = N > 1 ? N : 0; }
+    else if (nm == "z1z1_rem_xnn_s") { src = lv.z1z1; cnt = N > 1 ? N : 0; }
+    else throw Error(ERR_INVALID_ARG, "unknown table name");
+    if (nm != "f" && cnt && !src) throw Error(ERR_MISSING_TABLES, "table was not built");
+    *count = cnt;
+    if (!out) return;
+    require(cap_elems >= cnt, ERR_BUFFER_TOO_SMALL, "table buffer too small");
+    Fp* m = io.alloc(cnt);
+    k::mul_const(m, src, fp_const_R(), cnt, io.st);  // plain -> Montgomery, the reference's in-memory form
+    io.out(out, m, cnt);
+  });
+}
+
+// ---- host-buffer algorithms -----------------------------------------------------------------
+#define LOCKED_IO                                              \
+  require(t != nullptr, ERR_INVALID_ARG, "null tree handle");  \
+  std::lock_guard<std::mutex> lock(const_cast<ecfft_tree*>(t)->mu); \
+  HostIO io(*t->tree);                                         \
+  Engine eng(*t->tree, io.st);
+
+int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t* evals) {
+  return guard([&] {
+    LOCKED_IO
+    eng.level_for(n);
+    Fp* d_in = io.in(coeffs, n);
+    Fp* d_out = io.alloc(n);
+    eng.enter(d_in, d_out, n);
+    io.out(evals, d_out, n);
+  });
+}
+int ecfft_exit(const ecfft_tree* t, const uint64_t* evals, size_t n, uint64_t* coeffs) {
+  return guard([&] {
+    LOCKED_IO
+    eng.level_for(n);
+    Fp* d_in = io.in(evals, n);
+    Fp* d_out = io.alloc(n);
+    eng.exit(d_in, d_out, n);
+    io.out(coeffs, d_out, n);
+  });
+}
+int ecfft_extend(const ecfft_tree* t, const uint64_t* evals, size_t n, int moiety, uint64_t* out) {
+  return guard([&] {
+    LOCKED_IO
+    require(moiety == 0 || moiety == 1, ERR_INVALID_ARG, "bad moiety");
+    require(n > 0 && n <= ((size_t)1 << 62), ERR_NOT_POW2, "bad length");
+    eng.level_for(2 * n);
+    Fp* d = io.in(evals, n);
+    eng.extend(d, d, n, 1, (Moiety)moiety);
+    io.out(out, d, n);
+  });
+}
+int ecfft_mextend(const ecfft_tree* t, const uint64_t* evals, size_t n, int moiety, uint64_t* out) {
+  return guard([&] {
+    LOCKED_IO
+    require(moiety == 0 || moiety == 1, ERR_INVALID_ARG, "bad moiety");
+    require(n > 0 && n <= ((size_t)1 << 62), ERR_NOT_POW2, "bad length");
+    eng.level_for(2 * n);
+    Fp* d = io.in(evals, n);
+    eng.mextend(d, d, n, (Moiety)moiety, FORM_MONT);
+    io.out(out, d, n);
+  });
+}
+int ecfft_degree(const ecfft_tree* t, const uint64_t* evals, size_t n, size_t* degree) {
+  return guard([&] {
+    LOCKED_IO
+    require(degree != nullptr, ERR_INVALID_ARG, "null degree");
+    eng.level_for(n);
+    Fp* d = io.in(evals, n);
+    *degree = eng.degree(d, n);
+  });
+}
+static int redc_host(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, size_t n, uint64_t* out, Moiety m) {
+  return guard([&] {
+    LOCKED_IO
+    eng.level_for(n);
+    Fp* d = io.in(evals, n);
+    Fp* da = io.in(a, n);
+    Fp* o = io.alloc(n);
+    eng.redc_user(d, da, n, m, o);
+    io.out(out, o, n);
+  });
+}
+int ecfft_redc_z0(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, size_t n, uint64_t* out) { return redc_host(t, evals, a, n, out, S0); }
+int ecfft_redc_z1(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, size_t n, uint64_t* out) { return redc_host(t, evals, a, n, out, S1); }
+int ecfft_modular_reduce(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, const uint64_t* c, size_t n, uint64_t* out) {
+  return guard([&] {
+    LOCKED_IO
+    eng.level_for(n);
+    Fp* d = io.in(evals, n);
+    Fp* da = io.in(a, n);
+    Fp* dc = io.in(c, n);
+    Fp* o = io.alloc(n);
+    eng.mod_user(d, da, dc, n, o);
+    io.out(out, o, n);
+  });
+}
+int ecfft_vanish(const ecfft_tree* t, const uint64_t* vanish_domain, size_t n, uint64_t* out) {
+  return guard([&] {
+    LOCKED_IO
+    require(n > 0 && n <= ((size_t)1 << 62), ERR_NOT_POW2, "bad length");
+    eng.level_for(2 * n);
+    Fp* d = io.in(vanish_domain, n);
+    Fp* o = io.alloc(2 * n);
+    eng.vanish(d, o, n, FORM_MONT);
+    io.out(out, o, 2 * n);
+  });
+}
+
+// ---- device-buffer algorithms -----------------------------------------------------------------
+#define DEV_ENGINE                                             \
+  require(t != nullptr, ERR_INVALID_ARG, "null tree handle");  \
+  ECFFT_CUDA(cudaSetDevice(t->tree->device));                  \
+  Engine eng(*t->tree, pick_stream(t, stream));
+
+int ecfft_enter_dev(const ecfft_tree* t, const void* d_coeffs, size_t n, void* d_evals, void* stream) {
+  return guard([&] { DEV_ENGINE eng.enter(dptr(d_coeffs), dptr(d_evals), n); });
+}
+int ecfft_enter_range_dev(const ecfft_tree* t, const void* d_in, size_t n, size_t m_lo, size_t m_hi, void* d_out, void* stream) {
+  return guard([&] { DEV_ENGINE eng.enter_range(dptr(d_in), dptr(d_out), n, m_lo, m_hi); });
+}
+int ecfft_exit_dev(const ecfft_tree* t, const void* d_evals, size_t n, void* d_coeffs, void* stream) {
+  return guard([&] { DEV_ENGINE eng.exit(dptr(d_evals), dptr(d_coeffs), n); });
+}
+int ecfft_extend_dev(const ecfft_tree* t, const void* d_evals, size_t n, int moiety, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    require(moiety == 0 || moiety == 1, ERR_INVALID_ARG, "bad moiety");
+    require(n > 0 && n <= ((size_t)1 << 62), ERR_NOT_POW2, "bad length");
+    eng.extend(dptr(d_evals), dptr(d_out), n, 1, (Moiety)moiety);
+  });
+}
+int ecfft_mextend_dev(const ecfft_tree* t, const void* d_evals, size_t n, int moiety, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    require(moiety == 0 || moiety == 1, ERR_INVALID_ARG, "bad moiety");
+    require(n > 0 && n <= ((size_t)1 << 62), ERR_NOT_POW2, "bad length");
+    eng.mextend(dptr(d_evals), dptr(d_out), n, (Moiety)moiety, FORM_MONT);
+  });
+}
+int ecfft_degree_dev(const ecfft_tree* t, const void* d_evals, size_t n, size_t* degree, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    require(degree != nullptr, ERR_INVALID_ARG, "null degree");
+    *degree = eng.degree(dptr(d_evals), n);
+  });
+}
+int ecfft_redc_z0_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, size_t n, void* d_out, void* stream) {
+  return guard([&] { DEV_ENGINE eng.redc_user(dptr(d_evals), dptr(d_a), n, S0, dptr(d_out)); });
+}
+int ecfft_redc_z1_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, size_t n, void* d_out, void* stream) {
+  return guard([&] { DEV_ENGINE eng.redc_user(dptr(d_evals), dptr(d_a), n, S1, dptr(d_out)); });
+}
+int ecfft_modular_reduce_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, const void* d_c, size_t n, void* d_out, void* stream) {
+  return guard([&] { DEV_ENGINE eng.mod_user(dptr(d_evals), dptr(d_a), dptr(d_c), n, dptr(d_out)); });
+}
+int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    require(n > 0 && n <= ((size_t)1 << 62), ERR_NOT_POW2, "bad length");
+    eng.vanish(dptr(d_domain), dptr(d_out), n, FORM_MONT);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,271 @@
+// The FFTree<F> algorithms (reference src/fftree.rs:72-316) as host-side schedules of batched
+// device kernels.  The reference recurses on Vec<F>; here every recursion depth is one batched
+// launch over all sub-problems of that depth (they share the chain level's tables):
+//   ENTER / VANISH run bottom-up, EXIT runs top-down, DEGREE follows its single branch.
+#include "engine.h"
+
+namespace ecfft {
+
+static inline bool is_pow2(size_t n) { return n && !(n & (n - 1)); }
+static inline uint32_t ilog2(size_t n) {
+  uint32_t l = 0;
+  while (n >>= 1) l++;
+  return l;
+}
+
+Tree::~Tree() {
+  cudaSetDevice(device);
+  for (void* p : owned) cudaFree(p);
+  if (stream) cudaStreamDestroy(stream);
+}
+Fp* Tree::dalloc(size_t count) {
+  void* p = nullptr;
+  ECFFT_CUDA(cudaMalloc(&p, (count ? count : 1) * sizeof(Fp)));
+  owned.push_back(p);
+  return (Fp*)p;
+}
+
+// subtree_with_size, reference src/fftree.rs:489-496
+const Level& Engine::level_for(size_t leaves) const {
+  if (!is_pow2(leaves)) throw Error(ERR_NOT_POW2, "length is not a power of two");
+  uint32_t lg = ilog2(leaves);
+  if (lg > t.log_n) throw Error(ERR_TREE_TOO_SMALL, "FFTree is too small");
+  return t.levels[lg];
+}
+
+Fp* Engine::tmp(size_t count) const {
+  void* p = nullptr;
+  ECFFT_CUDA(cudaMallocAsync(&p, (count ? count : 1) * sizeof(Fp), st));
+  return (Fp*)p;
+}
+void Engine::release(Fp* p) const {
+  if (p) ECFFT_CUDA(cudaFreeAsync(p, st));
+}
+
+// FFTree::extend, src/fftree.rs:123-126 (batched)
+void Engine::extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target) const {
+  const Level& lv = level_for(h * 2);
+  k::extend(lv, in, out, ilog2(h), nvec, target, st);
+}
+
+// FFTree::enter_impl, src/fftree.rs:143-161, flattened bottom-up: after the pass for m the
+// array holds n/m evaluation vectors of length m (one per coefficient chunk).
+void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
+  if (!is_pow2(n) || !is_pow2(m_lo) || !is_pow2(m_hi)) throw Error(ERR_NOT_POW2, "length is not a power of two");
+  if (m_hi > n || m_lo > m_hi) throw Error(ERR_INVALID_ARG, "enter: bad level range");
+  level_for(m_hi);
+  if (m_lo == m_hi) {
+    if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  Fp* W = tmp(n);
+  Fp* ping[2] = {nullptr, nullptr};
+  const Fp* cur = in;
+  uint32_t idx = 0;
+  for (size_t m = m_lo * 2; m <= m_hi; m *= 2, idx++) {
+    const Level& lv = level_for(m);
+    const size_t h = m / 2;
+    Fp* dst;
+    if (m == m_hi && out != in) {
+      dst = out;
+    } else {
+      if (!ping[idx & 1]) ping[idx & 1] = tmp(n);
+      dst = ping[idx & 1];
+    }
+    k::extend(lv, cur, W, ilog2(h), n / h, S1, st);  // u1, v1 for every block at once
+    k::enter_combine(cur, W, lv.xnn_s, dst, ilog2(h), n, st);
+    cur = dst;
+  }
+  if (cur != out) ECFFT_CUDA(cudaMemcpyAsync(out, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+  release(W);
+  release(ping[0]);
+  release(ping[1]);
+}
+
+// FFTree::redc_impl, src/fftree.rs:232-259, for nvec vectors of length len sharing `a`
+// (plain form).  a0inv (= 1/a[2i], plain) may be supplied when already known.
+void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out) const {
+  const Level& lv = level_for(len);
+  if (len < 2) throw Error(ERR_INVALID_ARG, "redc: length must be >= 2");
+  const Fp* zinv = moiety == S0 ? lv.z0_inv_s1 : lv.z1_inv_s0;
+  if (!zinv) throw Error(ERR_MISSING_TABLES, "redc: tree was built without the Z tables");
+  const size_t h = len / 2;
+  const uint32_t log_h = ilog2(h);
+  Fp* a0inv_own = nullptr;
+  if (!a0inv_or_null) {
+    a0inv_own = tmp(h);
+    k::copy_strided(a0inv_own, a_plain, h, 2, st);
+    k::batch_inverse(a0inv_own, h, st);
+    a0inv_or_null = a0inv_own;
+  }
+  Fp* t0 = tmp(h * nvec);
+  Fp* g1 = tmp(h * nvec);
+  k::redc_pre(t0, evals, a0inv_or_null, h, nvec, st);
+  k::extend(lv, t0, g1, log_h, nvec, moiety == S1 ? S0 : S1, st);
+  Fp* h1 = t0;  // t0 is dead once g1 exists
+  k::redc_mid(h1, evals, g1, a_plain, zinv, h, nvec, st);
+  Fp* h0 = g1;
+  k::extend(lv, h1, h0, log_h, nvec, moiety, st);
+  k::interleave(out, h0, h1, h * nvec, st);
+  release(t0);
+  release(g1);
+  release(a0inv_own);
+}
+
+// FFTree::modular_reduce_impl, src/fftree.rs:277-281
+void Engine::modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, const Fp* c_plain, size_t len, size_t nvec, Fp* out) const {
+  const size_t h = len / 2;
+  Fp* a0inv_own = nullptr;
+  if (!a0inv_or_null) {
+    a0inv_own = tmp(h);
+    k::copy_strided(a0inv_own, a_plain, h, 2, st);
+    k::batch_inverse(a0inv_own, h, st);
+    a0inv_or_null = a0inv_own;
+  }
+  Fp* hb = tmp(len * nvec);
+  redc(evals, a_plain, a0inv_or_null, len, nvec, S0, hb);
+  k::mul_bcast(hb, hb, c_plain, len, nvec, st);
+  redc(hb, a_plain, a0inv_or_null, len, nvec, S0, out);
+  release(hb);
+  release(a0inv_own);
+}
+
+// FFTree::exit_impl, src/fftree.rs:200-224, flattened top-down: before the pass for m the array
+// holds n/m evaluation vectors of length m; the pass replaces each by [u0 | v0].
+void Engine::exit(const Fp* evals, Fp* out, size_t n) const {
+  level_for(n);
+  if (n == 1) {
+    if (evals != out) ECFFT_CUDA(cudaMemcpyAsync(out, evals, sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  Fp* cur = tmp(n);
+  Fp* nxt = tmp(n);
+  Fp* M = tmp(n);
+  ECFFT_CUDA(cudaMemcpyAsync(cur, evals, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+  for (size_t m = n; m >= 2; m /= 2) {
+    const Level& lv = level_for(m);
+    if (!lv.z0z0) throw Error(ERR_MISSING_TABLES, "exit: tree was built without the Z tables");
+    const size_t h = m / 2, nvec = n / m;
+    // the reference batch-inverts xnn_s[::2] on every call (fftree.rs:235); the stored
+    // xnn_s_inv holds the same values
+    Fp* a0inv = tmp(h);
+    k::copy_strided(a0inv, lv.xnn_s_inv, h, 2, st);
+    modular_reduce(cur, lv.xnn_s, a0inv, lv.z0z0, m, nvec, M);
+    k::exit_split(nxt, cur, M, lv.xnn_s_inv, h, nvec, st);
+    release(a0inv);
+    Fp* sw = cur;
+    cur = nxt;
+    nxt = sw;
+  }
+  ECFFT_CUDA(cudaMemcpyAsync(out, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+  release(cur);
+  release(nxt);
+  release(M);
+}
+
+// FFTree::mextend_impl, src/fftree.rs:128-135
+void Engine::mextend(const Fp* in, Fp* out, size_t h, Moiety target, DataForm form) const {
+  const Level& lv = level_for(h * 2);
+  const Fp* z = target == S1 ? lv.z0_s1 : lv.z1_s0;
+  if (!z) throw Error(ERR_MISSING_TABLES, "mextend: tree was built without the Z tables");
+  k::extend(lv, in, out, ilog2(h), 1, target, st);
+  k::add_bcast_scaled(out, out, z, form == FORM_MONT ? fp_const_R() : fp_one(), h, 1, st);
+}
+
+// FFTree::degree_impl, src/fftree.rs:169-192
+size_t Engine::degree(const Fp* evals, size_t n) const {
+  level_for(n);
+  if (n == 1) return 0;
+  Fp* e0 = tmp(n / 2);
+  Fp* e1 = tmp(n / 2);
+  Fp* g1 = tmp(n / 2);
+  Fp* curbuf = tmp(n);
+  unsigned long long* counter = nullptr;
+  ECFFT_CUDA(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), st));
+  const Fp* cur = evals;
+  size_t len = n, result = 0;
+  while (len > 1) {
+    const Level& lv = level_for(len);
+    if (!lv.z0_inv_s1) throw Error(ERR_MISSING_TABLES, "degree: tree was built without the Z tables");
+    const size_t h = len / 2;
+    k::deinterleave(e0, e1, cur, h, st);
+    k::extend(lv, e0, g1, ilog2(h), 1, S1, st);
+    ECFFT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
+    k::count_neq(counter, g1, e1, h, st);
+    unsigned long long diff = 0;
+    ECFFT_CUDA(cudaMemcpyAsync(&diff, counter, sizeof diff, cudaMemcpyDeviceToHost, st));
+    ECFFT_CUDA(cudaStreamSynchronize(st));
+    if (diff == 0) {
+      ECFFT_CUDA(cudaMemcpyAsync(curbuf, e0, h * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    } else {
+      k::sub_mul_bcast(e1, e1, g1, lv.z0_inv_s1, h, 1, st);  // t1
+      k::extend(lv, e1, curbuf, ilog2(h), 1, S0, st);         // t0
+      result += h;
+    }
+    cur = curbuf;
+    len = h;
+  }
+  release(e0);
+  release(e1);
+  release(g1);
+  release(curbuf);
+  ECFFT_CUDA(cudaFreeAsync(counter, st));
+  return result;
+}
+
+void Engine::redc_user(const Fp* evals, const Fp* a_mont, size_t n, Moiety moiety, Fp* out) const {
+  level_for(n);
+  Fp* a_plain = tmp(n);
+  k::mul_const(a_plain, a_mont, fp_const_RINV(), n, st);
+  redc(evals, a_plain, nullptr, n, 1, moiety, out);
+  release(a_plain);
+}
+void Engine::mod_user(const Fp* evals, const Fp* a_mont, const Fp* c_mont, size_t n, Fp* out) const {
+  level_for(n);
+  Fp* a_plain = tmp(n);
+  Fp* c_plain = tmp(n);
+  k::mul_const(a_plain, a_mont, fp_const_RINV(), n, st);
+  k::mul_const(c_plain, c_mont, fp_const_RINV(), n, st);
+  modular_reduce(evals, a_plain, nullptr, c_plain, n, 1, out);
+  release(a_plain);
+  release(c_plain);
+}
+
+// FFTree::vanish_impl, src/fftree.rs:291-308, bottom-up.  Products of two data values need the
+// plain domain, so Montgomery-form input is converted on entry and the result on exit.
+void Engine::vanish(const Fp* domain, Fp* out, size_t n, DataForm form) const {
+  level_for(2 * n);
+  if (t.log_n < 1) throw Error(ERR_TREE_TOO_SMALL, "FFTree is too small");
+  Fp* Q = tmp(2 * n);
+  Fp* Q2 = tmp(2 * n);
+  Fp* q0 = tmp(n);
+  Fp* e = tmp(n);
+  const Fp* dom = domain;
+  if (form == FORM_MONT) {
+    k::mul_const(e, domain, fp_const_RINV(), n, st);
+    dom = e;
+  }
+  // base case: the 2-leaf tree's leaves are f[n_top], f[n_top + n_top/2]
+  k::vanish_base(Q, dom, t.base_leaf0, t.base_leaf1, n, st);
+  for (size_t len = 2, cnt = n; cnt > 1; len *= 2, cnt /= 2) {
+    const Level& lv = level_for(2 * len);
+    if (!lv.z0_s1) throw Error(ERR_MISSING_TABLES, "vanish: tree was built without the Z tables");
+    const size_t pairs = cnt / 2;
+    k::mul_pairs(q0, Q, len, pairs, 0, st);
+    k::extend(lv, q0, e, ilog2(len), pairs, S1, st);
+    k::vanish_merge(Q2, q0, e, lv.z0_s1, fp_one(), len, pairs, st);
+    Fp* sw = Q;
+    Q = Q2;
+    Q2 = sw;
+  }
+  if (form == FORM_MONT)
+    k::mul_const(out, Q, fp_const_R(), 2 * n, st);
+  else
+    ECFFT_CUDA(cudaMemcpyAsync(out, Q, 2 * n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+  release(Q);
+  release(Q2);
+  release(q0);
+  release(e);
+}
+
+}  // namespace ecfft

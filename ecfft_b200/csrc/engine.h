@@ -1,0 +1,159 @@
+// Internal interface of the B200 ECFFT engine (not installed; the public boundary is
+// include/ecfft_b200.h).  Everything here works on DEVICE pointers to Fp arrays.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "fp.cuh"
+
+namespace ecfft {
+
+// status codes mirrored in include/ecfft_b200.h
+enum Status : int {
+  OK = 0,
+  ERR_NOT_POW2 = 1,        // reference: assert!(n.is_power_of_two()) fftree.rs:44,490
+  ERR_TREE_TOO_SMALL = 2,  // reference: panic!("FFTree is too small") fftree.rs:494
+  ERR_BAD_BYTES = 3,       // reference: SerializationError (truncated / element >= p)
+  ERR_CUDA = 4,
+  ERR_INVALID_ARG = 5,
+  ERR_TOO_LARGE = 6,       // reference: build_fftree returns None when log2 n >= 36, lib.rs:61-64
+  ERR_MISSING_TABLES = 7,  // tree built with ENTER-only tables asked for EXIT/REDC/...
+  ERR_BUFFER_TOO_SMALL = 8,
+};
+
+struct Error : std::runtime_error {
+  int code;
+  Error(int c, const std::string& m) : std::runtime_error(m), code(c) {}
+};
+
+#define ECFFT_CUDA(expr)                                                                          \
+  do {                                                                                            \
+    cudaError_t e__ = (expr);                                                                     \
+    if (e__ != cudaSuccess)                                                                       \
+      throw ::ecfft::Error(::ecfft::ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+
+enum Moiety : int { S0 = 0, S1 = 1 };  // reference fftree.rs:17-21, declaration order
+// Whether the DATA flowing through an op is in Montgomery form (public API) or plain form
+// (tree construction).  Tables are always plain.  Only additive constants and
+// data*data products care.
+enum DataForm : int { FORM_MONT = 0, FORM_PLAIN = 1 };
+
+// One level of the subtree chain: FFTree with N = 2^log_n leaves (reference fftree.rs:23-38).
+// All tables are device arrays of canonical plain-form Fp.  Matrices keep the reference's
+// BinaryTree layout: N entries of 4 Fp (row major), layer l at [ (N/2)>>l , 2*((N/2)>>l) ).
+struct Level {
+  uint32_t log_n = 0;
+  Fp* rmat = nullptr;       // N * 4
+  Fp* dmat = nullptr;       // N * 4
+  Fp* xnn_s = nullptr;      // N
+  Fp* xnn_s_inv = nullptr;  // N
+  Fp* z0_s1 = nullptr;      // N/2
+  Fp* z1_s0 = nullptr;
+  Fp* z0_inv_s1 = nullptr;
+  Fp* z1_inv_s0 = nullptr;
+  Fp* z0z0 = nullptr;       // N   <Z_0^2 mod X^(N/2) on S>
+  Fp* z1z1 = nullptr;       // N
+  bool has_z = false;       // z tables present (full build)
+};
+
+struct RatMapHost {  // reference utils.rs:367-371; coefficients low->high, plain canonical
+  std::vector<Fp> num, den;
+};
+
+enum BuildParts : int { PARTS_FULL = 0, PARTS_ENTER_ONLY = 1 };
+
+struct Tree {
+  int device = 0;
+  uint32_t log_n = 0;                // top level
+  Fp* f = nullptr;                   // top-level BinaryTree<F>, 2n entries (f[0] = 0)
+  std::vector<Level> levels;         // levels[k] has 2^k leaves, k = 0..log_n
+  std::vector<RatMapHost> maps;      // log_n rational maps (level k uses the first k)
+  int parts = PARTS_FULL;
+  Fp base_leaf0, base_leaf1;         // leaves of the 2-leaf chain level (VANISH base case, fftree.rs:293-298)
+  cudaStream_t stream = nullptr;     // default stream for host-buffer calls
+  std::vector<void*> owned;          // device allocations to free
+  ~Tree();
+  Fp* dalloc(size_t count);          // owned device allocation of `count` Fp
+  size_t n() const { return (size_t)1 << log_n; }
+};
+
+// ---- kernels.cu: launchers (all asynchronous on `st`) -------------------------------------
+namespace k {
+// EXTEND of `nvec` contiguous vectors of length h = 2^log_h on the level with 2h leaves,
+// towards `target`; in may equal out.
+void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st);
+// ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks
+void enter_combine(const Fp* A, const Fp* W, const Fp* xnn, Fp* out, uint32_t log_h, size_t n, cudaStream_t st);
+
+void mul_const(Fp* out, const Fp* in, Fp c, size_t n, cudaStream_t st);                       // out = in*c
+void mul_bcast(Fp* out, const Fp* in, const Fp* c, size_t len, size_t nvec, cudaStream_t st); // out[v][i] = in[v][i]*c[i]
+void add_bcast_scaled(Fp* out, const Fp* in, const Fp* z, Fp scale, size_t len, size_t nvec, cudaStream_t st);  // out = in + z*scale
+void deinterleave(Fp* even, Fp* odd, const Fp* in, size_t pairs, cudaStream_t st);
+void interleave(Fp* out, const Fp* even, const Fp* odd, size_t pairs, cudaStream_t st);
+void copy_strided(Fp* out, const Fp* in, size_t count, size_t in_stride, cudaStream_t st);   // out[i] = in[i*stride]
+// REDC pieces (fftree.rs:232-259), vectors of length 2h, a/zinv shared by all vectors
+void redc_pre(Fp* t0, const Fp* evals, const Fp* a0inv, size_t h, size_t nvec, cudaStream_t st);
+void redc_mid(Fp* h1, const Fp* evals, const Fp* g1, const Fp* a, const Fp* zinv, size_t h, size_t nvec, cudaStream_t st);
+// EXIT split (fftree.rs:206-220): next[v] = [ M[v][::2] | (e[v][::2]-M[v][::2]) * xnn_inv[::2] ]
+void exit_split(Fp* next, const Fp* evals, const Fp* M, const Fp* xnn_inv, size_t h, size_t nvec, cudaStream_t st);
+// VANISH pieces (fftree.rs:291-308)
+void vanish_base(Fp* out, const Fp* dom, Fp l0, Fp l1, size_t n, cudaStream_t st);            // out[2i] = a-l0, out[2i+1] = a-l1
+void mul_pairs(Fp* q0, const Fp* Q, size_t len, size_t npairs, int fix_mont, cudaStream_t st); // q0[w] = Q[2w]*Q[2w+1]
+void vanish_merge(Fp* out, const Fp* q0, const Fp* e, const Fp* z, Fp zscale, size_t len, size_t nvec, cudaStream_t st);
+// DEGREE pieces (fftree.rs:169-192)
+void count_neq(unsigned long long* counter, const Fp* a, const Fp* b, size_t n, cudaStream_t st);
+void sub_mul_bcast(Fp* out, const Fp* a, const Fp* b, const Fp* c, size_t len, size_t nvec, cudaStream_t st);  // (a-b)*c
+// generic helpers
+void pow_u64(Fp* out, const Fp* in, uint64_t e, size_t n, cudaStream_t st);
+void batch_inverse(Fp* v, size_t n, cudaStream_t st);  // in place; zeros stay zero (ark_ff::batch_inversion)
+void count_noncanonical(unsigned long long* counter, const Fp* v, size_t n, cudaStream_t st);
+void fill(Fp* out, Fp c, size_t n, cudaStream_t st);
+void sqr_sub_mul(Fp* out, const Fp* z_half, int z_parity, const Fp* xnn, const Fp* sub, const Fp* mul, size_t n, cudaStream_t st);
+void muladd(Fp* out, const Fp* a, const Fp* b, const Fp* c, size_t n, cudaStream_t st);  // out = a + b*c
+// tree construction
+void build_leaves(Fp* leaves, size_t n, Fp a, Fp a4, Fp offx, Fp offy, const Fp* gtab_xy /* log n points: 2^j * G */, uint32_t log_n, cudaStream_t st);
+void ratmap_layer(Fp* layer, const Fp* prev, size_t count, const Fp* num, int nnum, const Fp* den, int nden, cudaStream_t st);
+void build_matrices(Fp* rmat_layer, Fp* dmat_layer, const Fp* flayer, size_t fstride, size_t d, const Fp* den, int nden, cudaStream_t st);
+}  // namespace k
+
+// ---- engine.cu: the algorithms on device buffers ------------------------------------------
+struct Engine {
+  const Tree& t;
+  cudaStream_t st;
+  Engine(const Tree& tree, cudaStream_t s) : t(tree), st(s) {}
+  const Level& level_for(size_t leaves) const;  // subtree_with_size; throws like the reference panics
+
+  // scratch (stream-ordered)
+  Fp* tmp(size_t count) const;
+  void release(Fp* p) const;
+
+  // batched primitives: nvec contiguous vectors
+  void extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target) const;
+  void redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out) const;
+  void modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, const Fp* c_plain, size_t len, size_t nvec, Fp* out) const;
+
+  // the FFTree<F> surface (fftree.rs:72-316) on device buffers
+  void enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // bottom-up levels m_lo < m <= m_hi
+  void enter(const Fp* coeffs, Fp* out, size_t n) const { enter_range(coeffs, out, n, 1, n); }
+  void exit(const Fp* evals, Fp* out, size_t n) const;
+  void mextend(const Fp* in, Fp* out, size_t h, Moiety target, DataForm form) const;
+  size_t degree(const Fp* evals, size_t n) const;
+  void redc_user(const Fp* evals, const Fp* a_mont, size_t n, Moiety moiety, Fp* out) const;
+  void mod_user(const Fp* evals, const Fp* a_mont, const Fp* c_mont, size_t n, Fp* out) const;
+  void vanish(const Fp* domain, Fp* out, size_t n, DataForm form) const;
+};
+
+// ---- builder.cu / serialize.cu --------------------------------------------------------------
+Tree* build_secp256k1(size_t n, int parts, int device);                                     // lib.rs:39-85
+Tree* tree_from_leaves(const Fp* leaves_dev_plain, size_t n, const std::vector<RatMapHost>& maps, int parts, int device);  // fftree.rs:42-70
+void finish_tree(Tree& t);                                                                  // fftree.rs:318-463 for every chain level
+size_t serialized_size(const Tree& t, bool compressed);
+size_t serialize(const Tree& t, bool compressed, uint8_t* buf, size_t cap);
+Tree* deserialize(const uint8_t* buf, size_t len, bool compressed, int device);
+
+}  // namespace ecfft

@@ -138,7 +138,7 @@ FP_HD uint32_t madc_hi(uint32_t a, uint32_t b, uint32_t c) {
 #define FP_PX 0xFFFFFFFFu
 #define FP_MONT_NP0 0xD2253531u  // -p^-1 mod 2^32
 
-struct Fp {
+struct alignas(16) Fp {
   uint32_t v[8];
 };
 
@@ -435,22 +435,49 @@ FP_HD Fp fp_pow_u64(const Fp& x, uint64_t e) {
   return fp_canon(r);
 }
 
-// x^(p-2) (Fermat inverse); 0 -> 0.  p-2 = 2^256 - 2^32 - 979
-FP_HD Fp fp_inv(const Fp& x) {
-  // exponent limbs (LE u32): 0xFFFFFC2D, 0xFFFFFFFE, 0xFFFFFFFF x6
-  Fp r = fp_one();
-  bool started = false;
-  for (int l = 7; l >= 0; l--) {
-    uint32_t w = (l == 0) ? 0xFFFFFC2Du : (l == 1 ? 0xFFFFFFFEu : 0xFFFFFFFFu);
-    for (int i = 31; i >= 0; i--) {
-      if (started) r = fp_mul_lazy(r, r);
-      if ((w >> i) & 1) {
-        r = started ? fp_mul_lazy(r, x) : x;
-        started = true;
-      }
-    }
-  }
-  return fp_canon(r);
+// n squarings
+FP_HD Fp fp_sqr_n(Fp x, int n) {
+  for (int i = 0; i < n; i++) x = fp_mul_lazy(x, x);
+  return x;
+}
+// x^(p-2) (Fermat inverse); 0 -> 0.  p-2 in binary is 223 ones, a zero, 22 ones, 0000, 1, 0, 11, 0, 1:
+// blocks of ones of length {1,2,22,223} -> addition chain with 255 squarings + 15 multiplications.
+FP_HD Fp fp_inv(const Fp& a) {
+  Fp x2 = fp_mul_lazy(fp_sqr_n(a, 1), a);
+  Fp x3 = fp_mul_lazy(fp_sqr_n(x2, 1), a);
+  Fp x6 = fp_mul_lazy(fp_sqr_n(x3, 3), x3);
+  Fp x9 = fp_mul_lazy(fp_sqr_n(x6, 3), x3);
+  Fp x11 = fp_mul_lazy(fp_sqr_n(x9, 2), x2);
+  Fp x22 = fp_mul_lazy(fp_sqr_n(x11, 11), x11);
+  Fp x44 = fp_mul_lazy(fp_sqr_n(x22, 22), x22);
+  Fp x88 = fp_mul_lazy(fp_sqr_n(x44, 44), x44);
+  Fp x176 = fp_mul_lazy(fp_sqr_n(x88, 88), x88);
+  Fp x220 = fp_mul_lazy(fp_sqr_n(x176, 44), x44);
+  Fp x223 = fp_mul_lazy(fp_sqr_n(x220, 3), x3);
+  Fp t = fp_mul_lazy(fp_sqr_n(x223, 23), x22);
+  t = fp_mul_lazy(fp_sqr_n(t, 5), a);
+  t = fp_mul_lazy(fp_sqr_n(t, 3), x2);
+  t = fp_mul_lazy(fp_sqr_n(t, 2), a);
+  return fp_canon(t);
+}
+// x^((p+1)/4): square root candidate for p = 3 (mod 4) (ark-ff Case3Mod4); caller checks r*r == x.
+// (p+1)/4 = 2^254 - 2^30 - 244: 223 ones, 0, 22 ones, 0000, 11, 00
+FP_HD Fp fp_sqrt_candidate(const Fp& a) {
+  Fp x2 = fp_mul_lazy(fp_sqr_n(a, 1), a);
+  Fp x3 = fp_mul_lazy(fp_sqr_n(x2, 1), a);
+  Fp x6 = fp_mul_lazy(fp_sqr_n(x3, 3), x3);
+  Fp x9 = fp_mul_lazy(fp_sqr_n(x6, 3), x3);
+  Fp x11 = fp_mul_lazy(fp_sqr_n(x9, 2), x2);
+  Fp x22 = fp_mul_lazy(fp_sqr_n(x11, 11), x11);
+  Fp x44 = fp_mul_lazy(fp_sqr_n(x22, 22), x22);
+  Fp x88 = fp_mul_lazy(fp_sqr_n(x44, 44), x44);
+  Fp x176 = fp_mul_lazy(fp_sqr_n(x88, 88), x88);
+  Fp x220 = fp_mul_lazy(fp_sqr_n(x176, 44), x44);
+  Fp x223 = fp_mul_lazy(fp_sqr_n(x220, 3), x3);
+  Fp t = fp_mul_lazy(fp_sqr_n(x223, 23), x22);
+  t = fp_mul_lazy(fp_sqr_n(t, 6), x2);
+  t = fp_sqr_n(t, 2);
+  return fp_canon(t);
 }
 
 #if defined(__CUDACC__)

@@ -1,0 +1,112 @@
+/* ecfft_b200 — C ABI of the B200-native ECFFT engine.
+ *
+ * Drop-in boundary for the hot path of andrewmilson/ecfft: the inherent method surface of
+ * `FFTree<secp256k1::Fp>` (reference src/fftree.rs:41-497, re-exported src/lib.rs:10-11),
+ * `FftreeField::build_fftree` (src/lib.rs:14-16, 39-85) and the CanonicalSerialize /
+ * CanonicalDeserialize layout (src/fftree.rs:510-660).  The reference has no FFI of its own;
+ * these are the entry points a Rust shim over `FFTree<Fp>` binds (INTEGRATION.md shows it).
+ *
+ * Data layout (identical to the reference's in-memory layout so a shim can pass
+ * `slice.as_ptr() as *const u64`): a field element is 4 x u64 little-endian limbs in
+ * MONTGOMERY form (ark-ff `Fp256<MontBackend<FqConfig,4>>`, src/lib.rs:37), vectors are
+ * contiguous arrays of such elements.  Moiety: 0 = S0, 1 = S1 (src/fftree.rs:17-21).
+ * Outputs are written to caller-allocated buffers; the library keeps no reference to caller
+ * memory after a call returns.
+ *
+ * Errors: the reference panics ("TODO: errors", src/fftree.rs:40); every entry point here
+ * returns a status instead and never aborts.  ecfft_last_error() describes the last failure
+ * on the calling thread.
+ *
+ * `*_dev` variants take DEVICE pointers (16-byte aligned) and a cudaStream_t (as void*, NULL =
+ * the handle's own stream); they only enqueue work and do not synchronise.
+ */
+#ifndef ECFFT_B200_H
+#define ECFFT_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECFFT_OK 0
+#define ECFFT_ERR_NOT_POW2 1         /* assert!(n.is_power_of_two())      src/fftree.rs:44,490  */
+#define ECFFT_ERR_TREE_TOO_SMALL 2   /* panic!("FFTree is too small")     src/fftree.rs:494     */
+#define ECFFT_ERR_BAD_BYTES 3        /* SerializationError                src/fftree.rs:602-660 */
+#define ECFFT_ERR_CUDA 4
+#define ECFFT_ERR_INVALID_ARG 5
+#define ECFFT_ERR_TOO_LARGE 6        /* build_fftree -> None, log2 n >= 36  src/lib.rs:61-64    */
+#define ECFFT_ERR_MISSING_TABLES 7   /* handle built with ECFFT_PARTS_ENTER_ONLY               */
+#define ECFFT_ERR_BUFFER_TOO_SMALL 8
+
+#define ECFFT_S0 0
+#define ECFFT_S1 1
+
+#define ECFFT_PARTS_FULL 0        /* every field of FFTree, as the reference builds it          */
+#define ECFFT_PARTS_ENTER_ONLY 1  /* f, matrices, xnn_s(_inv): what ENTER / EXTEND touch        */
+
+typedef struct ecfft_tree ecfft_tree; /* FFTree<Fp> resident in one GPU's HBM, src/fftree.rs:23-38 */
+
+const char* ecfft_last_error(void);
+int ecfft_device_count(int* count);
+
+/* ---- construction / persistence ------------------------------------------------------- */
+/* <Fp as FftreeField>::build_fftree(n), src/lib.rs:39-85 */
+int ecfft_tree_build_secp256k1(size_t n, int parts, int device, ecfft_tree** out);
+/* FFTree::new(leaves, rational_maps), src/fftree.rs:42-70.  leaves: n Montgomery elements.
+ * Rational map i (src/utils.rs:367-371) is given by map_lens[2i] numerator and map_lens[2i+1]
+ * denominator coefficients (low -> high, Montgomery), all concatenated in map_coeffs. */
+int ecfft_tree_new(const uint64_t* leaves, size_t n, const uint64_t* map_coeffs, const size_t* map_lens,
+                   size_t nmaps, int parts, int device, ecfft_tree** out);
+/* CanonicalDeserialize::deserialize_{compressed,uncompressed}, src/fftree.rs:602-660 */
+int ecfft_tree_deserialize(const uint8_t* bytes, size_t len, int compressed, int device, ecfft_tree** out);
+/* CanonicalSerialize::serialized_size / serialize_with_mode, src/fftree.rs:510-591 */
+int ecfft_tree_serialized_size(const ecfft_tree* t, int compressed, size_t* size);
+int ecfft_tree_serialize(const ecfft_tree* t, int compressed, uint8_t* buf, size_t cap, size_t* written);
+void ecfft_tree_free(ecfft_tree* t);
+/* f.leaves().len() of the handle's top tree */
+size_t ecfft_tree_leaves(const ecfft_tree* t);
+int ecfft_tree_device(const ecfft_tree* t);
+/* Read one of the pub fields (src/fftree.rs:25-37) of subtree_with_size(subtree_leaves) as
+ * Montgomery elements.  name: "f" (2N), "recombine_matrices" / "decompose_matrices" (4N, row
+ * major), "xnn_s", "xnn_s_inv" (N), "z0_s1", "z1_s0", "z0_inv_s1", "z1_inv_s0" (N/2),
+ * "z0z0_rem_xnn_s", "z1z1_rem_xnn_s" (N).  out may be NULL to query *count only. */
+int ecfft_tree_table(const ecfft_tree* t, size_t subtree_leaves, const char* name, uint64_t* out,
+                     size_t cap_elems, size_t* count);
+
+/* ---- the FFTree<F> algorithms, host buffers ------------------------------------------- */
+int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t* evals);            /* :164 */
+int ecfft_exit(const ecfft_tree* t, const uint64_t* evals, size_t n, uint64_t* coeffs);             /* :227 */
+int ecfft_extend(const ecfft_tree* t, const uint64_t* evals, size_t n, int moiety, uint64_t* out);  /* :123 */
+int ecfft_mextend(const ecfft_tree* t, const uint64_t* evals, size_t n, int moiety, uint64_t* out); /* :138 */
+int ecfft_degree(const ecfft_tree* t, const uint64_t* evals, size_t n, size_t* degree);             /* :195 */
+/* a has n elements (the reference's zip would silently truncate a longer `a`) */
+int ecfft_redc_z0(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, size_t n, uint64_t* out); /* :264 */
+int ecfft_redc_z1(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, size_t n, uint64_t* out); /* :272 */
+int ecfft_modular_reduce(const ecfft_tree* t, const uint64_t* evals, const uint64_t* a, const uint64_t* c,
+                         size_t n, uint64_t* out);                                                   /* :286 */
+/* out has 2n elements */
+int ecfft_vanish(const ecfft_tree* t, const uint64_t* vanish_domain, size_t n, uint64_t* out);      /* :313 */
+
+/* ---- device-buffer variants (no PCIe traffic; enqueue only) --------------------------- */
+int ecfft_enter_dev(const ecfft_tree* t, const void* d_coeffs, size_t n, void* d_evals, void* stream);
+int ecfft_exit_dev(const ecfft_tree* t, const void* d_evals, size_t n, void* d_coeffs, void* stream);
+int ecfft_extend_dev(const ecfft_tree* t, const void* d_evals, size_t n, int moiety, void* d_out, void* stream);
+int ecfft_mextend_dev(const ecfft_tree* t, const void* d_evals, size_t n, int moiety, void* d_out, void* stream);
+int ecfft_degree_dev(const ecfft_tree* t, const void* d_evals, size_t n, size_t* degree, void* stream); /* synchronises */
+int ecfft_redc_z0_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, size_t n, void* d_out, void* stream);
+int ecfft_redc_z1_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, size_t n, void* d_out, void* stream);
+int ecfft_modular_reduce_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, const void* d_c,
+                             size_t n, void* d_out, void* stream);
+int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* d_out, void* stream);
+/* Multi-GPU building block (DESIGN.md "multi-GPU"): run only the bottom-up ENTER recursion
+ * depths whose block size m satisfies m_lo < m <= m_hi on an array of n elements that already
+ * holds n/m_lo evaluation vectors of length m_lo (m_lo = 1: raw coefficients).  Rank g runs
+ * (1, n/G] on its coefficient chunk, the chunks are all-gathered, then (n/G, n] finishes. */
+int ecfft_enter_range_dev(const ecfft_tree* t, const void* d_in, size_t n, size_t m_lo, size_t m_hi,
+                          void* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
