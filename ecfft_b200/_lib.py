@@ -30,6 +30,7 @@ SYMBOLS = [
     "ecfft_enter_dev", "ecfft_exit_dev", "ecfft_extend_dev", "ecfft_mextend_dev",
     "ecfft_degree_dev", "ecfft_redc_z0_dev", "ecfft_redc_z1_dev",
     "ecfft_modular_reduce_dev", "ecfft_vanish_dev", "ecfft_enter_range_dev",
+    "ecfft_launch_count", "ecfft_profile_enable", "ecfft_profile_read",
 ]
 
 
@@ -88,6 +89,12 @@ def load():
     L.ecfft_modular_reduce_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp]
     L.ecfft_vanish_dev.argtypes = [vp, vp, sz, vp, vp]
     L.ecfft_enter_range_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+    L.ecfft_launch_count.restype = ctypes.c_ulonglong
+    L.ecfft_launch_count.argtypes = []
+    L.ecfft_profile_enable.restype = None
+    L.ecfft_profile_enable.argtypes = [ci]
+    L.ecfft_profile_read.argtypes = [ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(ctypes.c_ulonglong)]
     _lib = L
     return L
 

@@ -38,7 +38,9 @@ static const Fp* dptr(const void* p) {
   return (const Fp*)p;
 }
 static Fp* dptr(void* p) { return (Fp*)dptr((const void*)p); }
-static cudaStream_t pick_stream(const ecfft_tree* t, void* stream) { return stream ? (cudaStream_t)stream : t->tree->stream; }
+// `_dev` entry points enqueue on exactly the stream they are given (NULL = the legacy default stream,
+// which is what torch's default stream is), so the caller's events and ordering apply.
+static cudaStream_t pick_stream(const ecfft_tree*, void* stream) { return (cudaStream_t)stream; }
 
 namespace {
 // scoped device buffer fed from / drained to host memory on the handle's stream
@@ -74,6 +76,15 @@ struct HostIO {
 extern "C" {
 
 const char* ecfft_last_error(void) { return g_last_error.c_str(); }
+
+unsigned long long ecfft_launch_count(void) { return prof::launches(); }
+void ecfft_profile_enable(int on) { prof::enable(on != 0); }
+int ecfft_profile_read(int kernel, double* ms, double* alg_bytes, unsigned long long* launches) {
+  return guard([&] {
+    require(kernel >= 0 && kernel < prof::NUM_KERNELS && ms && alg_bytes && launches, ERR_INVALID_ARG, "bad profile query");
+    prof::read((prof::Kernel)kernel, ms, alg_bytes, launches);
+  });
+}
 
 int ecfft_device_count(int* count) {
   return guard([&] {

@@ -82,6 +82,19 @@ struct Tree {
   size_t n() const { return (size_t)1 << log_n; }
 };
 
+// ---- instrumentation (bench.py): launch counter and optional per-launch CUDA-event timing of the
+// two hot kernels, with the ALGORITHMIC bytes (level-streaming model) each launch covers
+namespace prof {
+enum Kernel : int { EXTEND_TILE = 0, ENTER_COMBINE = 1, NUM_KERNELS = 2 };
+void count_launch();
+unsigned long long launches();
+void enable(bool on);
+bool enabled();
+void record_begin(Kernel k, double alg_bytes, cudaStream_t st);
+void record_end(cudaStream_t st);
+void read(Kernel k, double* ms, double* alg_bytes, unsigned long long* launches);  // synchronises; clears k's records
+}  // namespace prof
+
 // ---- kernels.cu: launchers (all asynchronous on `st`) -------------------------------------
 namespace k {
 // EXTEND of `nvec` contiguous vectors of length h = 2^log_h on the level with 2h leaves,

@@ -9,7 +9,59 @@
 #include "engine.h"
 #include "ec.cuh"
 
+#include <atomic>
+#include <mutex>
+
 namespace ecfft {
+
+namespace prof {
+struct Rec { Kernel k; double bytes; cudaEvent_t e0, e1; };
+static std::atomic<unsigned long long> g_launches{0};
+static std::atomic<bool> g_enabled{false};
+static std::mutex g_mu;
+static std::vector<Rec> g_recs;
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+unsigned long long launches() { return g_launches.load(); }
+void enable(bool on) { g_enabled.store(on); }
+bool enabled() { return g_enabled.load(); }
+void record_begin(Kernel k, double alg_bytes, cudaStream_t st) {
+  Rec r;
+  r.k = k;
+  r.bytes = alg_bytes;
+  ECFFT_CUDA(cudaEventCreate(&r.e0));
+  ECFFT_CUDA(cudaEventCreate(&r.e1));
+  ECFFT_CUDA(cudaEventRecord(r.e0, st));
+  std::lock_guard<std::mutex> lock(g_mu);
+  g_recs.push_back(r);
+}
+void record_end(cudaStream_t st) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  ECFFT_CUDA(cudaEventRecord(g_recs.back().e1, st));
+}
+void read(Kernel k, double* ms, double* alg_bytes, unsigned long long* n) {
+  std::lock_guard<std::mutex> lock(g_mu);
+  *ms = 0;
+  *alg_bytes = 0;
+  *n = 0;
+  std::vector<Rec> keep;
+  for (Rec& r : g_recs) {
+    if (r.k != k) {
+      keep.push_back(r);
+      continue;
+    }
+    float t = 0;
+    ECFFT_CUDA(cudaEventSynchronize(r.e1));
+    ECFFT_CUDA(cudaEventElapsedTime(&t, r.e0, r.e1));
+    *ms += t;
+    *alg_bytes += r.bytes;
+    *n += 1;
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  g_recs.swap(keep);
+}
+}  // namespace prof
+
 namespace k {
 
 static constexpr int NT = 256;              // threads per CTA for the tile kernel
@@ -31,6 +83,7 @@ template <class F>
 static void map(size_t n, cudaStream_t st, F f) {
   if (n == 0) return;
   k_map<<<grid_for(n, 256), 256, 0, st>>>(n, f);
+  prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 
@@ -139,7 +192,18 @@ static void launch_tile(const TileParams& p, cudaStream_t st) {
   }
   size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
   if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
+  const bool timed = prof::enabled();
+  if (timed) {
+    // algorithmic bytes: every fused level reads and writes each element once (64 B) and reads its
+    // 2^j matrices (128 B each) once
+    double levels = (double)(p.j_hi - p.j_lo) * (p.do_d + p.do_r);
+    double mats = 0;
+    for (uint32_t j = p.j_lo; j < p.j_hi; j++) mats += (double)(p.do_d + p.do_r) * 128.0 * (double)(1ull << j);
+    prof::record_begin(prof::EXTEND_TILE, levels * 64.0 * (double)p.total + mats, st);
+  }
   k_extend_tile<<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
+  if (timed) prof::record_end(st);
+  prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 
@@ -220,7 +284,11 @@ void enter_combine(const Fp* A, const Fp* W, const Fp* xnn, Fp* out, uint32_t lo
   size_t npairs = n / 2;
   unsigned grid = (unsigned)((npairs + 255) / 256);
   if (grid > 148u * 32u) grid = 148u * 32u;
+  const bool timed = prof::enabled();
+  if (timed) prof::record_begin(prof::ENTER_COMBINE, 128.0 * (double)n, st);  // u0,v0,u1,v1 / xnn / out
   k_enter_combine<<<grid, 256, 0, st>>>(A, W, xnn, out, log_h, npairs);
+  if (timed) prof::record_end(st);
+  prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 
@@ -399,6 +467,7 @@ void batch_inverse(Fp* v, size_t n, cudaStream_t st) {
   size_t blocks = (warps + 3) / 4;
   if (blocks > 148 * 16) blocks = 148 * 16;
   k_batch_inverse<<<(unsigned)blocks, 128, 0, st>>>(v, n);
+  prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 
@@ -433,6 +502,7 @@ __global__ void __launch_bounds__(128) k_build_leaves(Fp* leaves, size_t n, Fp a
 void build_leaves(Fp* leaves, size_t n, Fp a, Fp a4, Fp offx, Fp offy, const Fp* gtab_xy, uint32_t log_n, cudaStream_t st) {
   size_t threads = (n + LEAF_CHUNK - 1) / LEAF_CHUNK;
   k_build_leaves<<<(unsigned)((threads + 127) / 128), 128, 0, st>>>(leaves, n, a, a4, offx, offy, gtab_xy, log_n);
+  prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 

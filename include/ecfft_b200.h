@@ -17,8 +17,9 @@
  * returns a status instead and never aborts.  ecfft_last_error() describes the last failure
  * on the calling thread.
  *
- * `*_dev` variants take DEVICE pointers (16-byte aligned) and a cudaStream_t (as void*, NULL =
- * the handle's own stream); they only enqueue work and do not synchronise.
+ * `*_dev` variants take DEVICE pointers (16-byte aligned) and a cudaStream_t (as void*; NULL is
+ * the legacy default stream, exactly as in the CUDA runtime); they only enqueue work on that
+ * stream and do not synchronise.
  */
 #ifndef ECFFT_B200_H
 #define ECFFT_B200_H
@@ -105,6 +106,16 @@ int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* 
  * (1, n/G] on its coefficient chunk, the chunks are all-gathered, then (n/G, n] finishes. */
 int ecfft_enter_range_dev(const ecfft_tree* t, const void* d_in, size_t n, size_t m_lo, size_t m_hi,
                           void* d_out, void* stream);
+
+/* ---- instrumentation used by bench.py ------------------------------------------------- */
+/* kernels launched by this library since it was loaded */
+unsigned long long ecfft_launch_count(void);
+/* when enabled, every launch of the two hot kernels is bracketed by CUDA events on its stream */
+void ecfft_profile_enable(int on);
+#define ECFFT_KERNEL_EXTEND_TILE 0
+#define ECFFT_KERNEL_ENTER_COMBINE 1
+/* sums (and clears) the records of one kernel: device ms, algorithmic bytes, launches */
+int ecfft_profile_read(int kernel, double* ms, double* alg_bytes, unsigned long long* launches);
 
 #ifdef __cplusplus
 }

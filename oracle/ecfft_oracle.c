@@ -689,6 +689,39 @@ int orc_enter_mt(const orc_tree* t, const fe* coeffs, size_t n, fe* out, int thr
   enter_impl(s, coeffs, n, out, depth);
   return 0;
 }
+/* Bottom-up restatement of enter_impl for the recursion depths m_lo < m <= m_hi: `in` holds n/m_lo
+ * evaluation vectors of length m_lo (m_lo = 1: coefficients); after the pass for m it holds n/m vectors
+ * of length m.  orc_enter_range(t, c, n, 1, n, out) == orc_enter(t, c, n, out); used to check the flat
+ * schedule the CUDA path and the multi-GPU split rely on. */
+int orc_enter_range(const orc_tree* t, const fe* in, size_t n, size_t m_lo, size_t m_hi, fe* out) {
+  if (!is_pow2(n) || !is_pow2(m_lo) || !is_pow2(m_hi) || m_lo > m_hi || m_hi > n) return 1;
+  if (!orc_subtree_with_size(t, m_hi)) return 1;
+  fe* cur = fe_alloc(n);
+  fe* nxt = fe_alloc(n);
+  memcpy(cur, in, n * sizeof(fe));
+  for (size_t m = 2 * m_lo; m <= m_hi; m *= 2) {
+    const orc_tree* s = orc_subtree_with_size(t, m);
+    size_t h = m / 2;
+    fe *u1 = fe_alloc(h), *v1 = fe_alloc(h);
+    for (size_t off = 0; off < n; off += m) {
+      const fe *u0 = cur + off, *v0 = cur + off + h;
+      extend_impl(s, u0, h, 1, u1, 0);
+      extend_impl(s, v0, h, 1, v1, 0);
+      for (size_t i = 0; i < h; i++) {
+        fe p;
+        fe_mul(&p, &v0[i], &s->xnn_s[2 * i]);
+        fe_add(&nxt[off + 2 * i], &u0[i], &p);
+        fe_mul(&p, &v1[i], &s->xnn_s[2 * i + 1]);
+        fe_add(&nxt[off + 2 * i + 1], &u1[i], &p);
+      }
+    }
+    free(u1); free(v1);
+    fe* sw = cur; cur = nxt; nxt = sw;
+  }
+  memcpy(out, cur, n * sizeof(fe));
+  free(cur); free(nxt);
+  return 0;
+}
 int orc_exit(const orc_tree* t, const fe* evals, size_t n, fe* out) {
   const orc_tree* s = orc_subtree_with_size(t, n);
   if (!s || (n > 1 && !s->nzz)) return 1;

@@ -71,6 +71,9 @@ int orc_vanish(const orc_tree* t, const fe* domain, size_t n, fe* out /* 2n */);
  * (same arithmetic, same result; used as the all-cores CPU baseline). */
 int orc_enter_mt(const orc_tree* t, const fe* coeffs, size_t n, fe* out, int threads);
 
+/* bottom-up ENTER restricted to recursion depths with block size m_lo < m <= m_hi (schedule check) */
+int orc_enter_range(const orc_tree* t, const fe* in, size_t n, size_t m_lo, size_t m_hi, fe* out);
+
 /* CanonicalSerialize / CanonicalDeserialize, reference src/fftree.rs:510-660 */
 size_t orc_serialized_size(const orc_tree* t, int compressed);
 size_t orc_serialize(const orc_tree* t, int compressed, uint8_t* buf, size_t cap);

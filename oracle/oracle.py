@@ -48,6 +48,7 @@ def lib():
         for name in ("orc_enter", "orc_exit"):
             getattr(L, name).argtypes = [vp, vp, sz, vp]
         L.orc_enter_mt.argtypes = [vp, vp, sz, vp, ci]
+        L.orc_enter_range.argtypes = [vp, vp, sz, sz, sz, vp]
         for name in ("orc_extend", "orc_mextend"):
             getattr(L, name).argtypes = [vp, vp, sz, ci, vp]
         L.orc_degree.argtypes = [vp, vp, sz, ctypes.POINTER(sz)]
@@ -166,6 +167,12 @@ class OracleTree:
             self._run(lib().orc_enter, self._h, _ptr(x), len(x), _ptr(out))
         return out
 
+    def enter_range(self, data, m_lo, m_hi):
+        x = _in(data)
+        out = np.empty_like(x)
+        self._run(lib().orc_enter_range, self._h, _ptr(x), len(x), m_lo, m_hi, _ptr(out))
+        return out
+
     def exit(self, evals):
         x = _in(evals)
         out = np.empty_like(x)
@@ -225,7 +232,8 @@ class OracleTree:
 
 def random_elements(n, seed=1):
     """n uniform field elements as raw Montgomery limbs (splitmix64 counter PRNG)."""
-    idx = np.arange(4 * n, dtype=np.uint64) + np.uint64(seed) * np.uint64(0x9E3779B97F4A7C15)
+    base = (int(seed) * 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+    idx = np.arange(4 * n, dtype=np.uint64) + np.uint64(base)
     with np.errstate(over="ignore"):
         z = idx * np.uint64(0x9E3779B97F4A7C15) + np.uint64(0x9E3779B97F4A7C15)
         z = (z ^ (z >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)
