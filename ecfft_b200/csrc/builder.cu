@@ -118,6 +118,27 @@ Tree* tree_from_leaves(const Fp* leaves_dev_plain, size_t n, const std::vector<R
   return t;
 }
 
+// Normalised-butterfly tables of chain level k (DESIGN.md "twiddle form"), derived from the top
+// tree's f and the level's recombine matrices.
+void build_norm_tables(Tree& t, uint32_t k) {
+  if (k == 0) return;
+  const size_t n = t.n(), N = (size_t)1 << k, stride = n / N, hh = N / 2;
+  cudaStream_t st = t.stream;
+  Level& lv = t.levels[k];
+  for (int mu = 0; mu < 2; mu++) {
+    lv.tw_r[mu] = t.dalloc(2 * hh);
+    lv.tw_d[mu] = t.dalloc(2 * hh);
+    k::build_twiddles(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, st);
+    lv.gam[mu] = t.dalloc(hh);
+    lv.gami[mu] = t.dalloc(hh);
+    k::build_gamma(lv.gam[mu], lv.rmat, hh, mu, st);
+    ECFFT_CUDA(cudaMemcpyAsync(lv.gami[mu], lv.gam[mu], hh * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    k::batch_inverse(lv.gami[mu], hh, st);
+  }
+  lv.gx = t.dalloc(hh);
+  k::mul_strided(lv.gx, lv.gam[1], lv.xnn_s, 2, 1, hh, st);
+}
+
 // One level of from_tree (src/fftree.rs:318-463): N = 2^k leaves = every (n/N)-th leaf of the top
 // tree; its f layers are the same strided views of the top tree's layers (derive_subtree, :465-482).
 static void build_level(Tree& t, uint32_t k) {
@@ -171,6 +192,8 @@ static void build_level(Tree& t, uint32_t k) {
     ECFFT_CUDA(cudaStreamSynchronize(st));
     ECFFT_CUDA(cudaFreeAsync(den, st));
   }
+
+  build_norm_tables(t, k);
 
   if (t.parts == PARTS_ENTER_ONLY || N == 1) {
     eng.release(s);

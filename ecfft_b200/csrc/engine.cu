@@ -72,8 +72,11 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
       if (!ping[idx & 1]) ping[idx & 1] = tmp(n);
       dst = ping[idx & 1];
     }
-    k::extend(lv, cur, W, ilog2(h), n / h, S1, st);  // u1, v1 for every block at once
-    k::enter_combine(cur, W, lv.xnn_s, dst, ilog2(h), n, st);
+    // u1, v1 for every block at once; with the normalised tables the Gamma^1 scaling of the
+    // EXTEND output is folded into the combine
+    const bool unscaled = k::butterfly_mode() == 1 && lv.gx && lv.gam[1] && lv.tw_r[1] && lv.tw_d[0] && lv.gami[0];
+    k::extend(lv, cur, W, ilog2(h), n / h, S1, st, unscaled);
+    k::enter_combine(lv, cur, W, dst, ilog2(h), n, unscaled, st);
     cur = dst;
   }
   if (cur != out) ECFFT_CUDA(cudaMemcpyAsync(out, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));

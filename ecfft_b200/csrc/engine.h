@@ -59,6 +59,13 @@ struct Level {
   Fp* z0z0 = nullptr;       // N   <Z_0^2 mod X^(N/2) on S>
   Fp* z1z1 = nullptr;       // N
   bool has_z = false;       // z tables present (full build)
+  // Normalised-butterfly tables (DESIGN.md "twiddle form"), derived from f and rmat; h = N/2.
+  // Index (2^j + i) addresses butterfly i of the level with half-stride 2^j; moiety mu = 0/1.
+  Fp* tw_r[2] = {nullptr, nullptr};   // h entries of {s0, s1}: the two tree nodes the pair maps through
+  Fp* tw_d[2] = {nullptr, nullptr};   // h entries of {1/(s1-s0), -s0}
+  Fp* gam[2] = {nullptr, nullptr};    // h: accumulated scale Gamma^mu_p of the recombine network
+  Fp* gami[2] = {nullptr, nullptr};   // h: 1/Gamma^mu_p
+  Fp* gx = nullptr;                   // h: Gamma^1_i * xnn_s[2i+1] (ENTER combine)
 };
 
 struct RatMapHost {  // reference utils.rs:367-371; coefficients low->high, plain canonical
@@ -98,10 +105,15 @@ void read(Kernel k, double* ms, double* alg_bytes, unsigned long long* launches)
 // ---- kernels.cu: launchers (all asynchronous on `st`) -------------------------------------
 namespace k {
 // EXTEND of `nvec` contiguous vectors of length h = 2^log_h on the level with 2h leaves,
-// towards `target`; in may equal out.
-void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st);
-// ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks
-void enter_combine(const Fp* A, const Fp* W, const Fp* xnn, Fp* out, uint32_t log_h, size_t n, cudaStream_t st);
+// towards `target`; in may equal out.  With the normalised tables present (and
+// butterfly_mode() == 1) it runs the 2-multiplication butterflies; `unscaled_out` then leaves
+// the final Gamma scaling to the caller (ENTER folds it into its combine).
+void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st,
+            bool unscaled_out = false);
+int butterfly_mode();  // 1 = normalised (default), 0 = 2x2 matrices (ECFFT_B200_BUTTERFLY=matrix)
+// ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
+// scaling (lv.gam[1], lv.gx are used instead of xnn's odd entries).
+void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t log_h, size_t n, bool W_unscaled, cudaStream_t st);
 
 void mul_const(Fp* out, const Fp* in, Fp c, size_t n, cudaStream_t st);                       // out = in*c
 void mul_bcast(Fp* out, const Fp* in, const Fp* c, size_t len, size_t nvec, cudaStream_t st); // out[v][i] = in[v][i]*c[i]
@@ -132,6 +144,10 @@ void muladd(Fp* out, const Fp* a, const Fp* b, const Fp* c, size_t n, cudaStream
 void build_leaves(Fp* leaves, size_t n, Fp a, Fp a4, Fp offx, Fp offy, const Fp* gtab_xy /* log n points: 2^j * G */, uint32_t log_n, cudaStream_t st);
 void ratmap_layer(Fp* layer, const Fp* prev, size_t count, const Fp* num, int nnum, const Fp* den, int nden, cudaStream_t st);
 void build_matrices(Fp* rmat_layer, Fp* dmat_layer, const Fp* flayer, size_t fstride, size_t d, const Fp* den, int nden, cudaStream_t st);
+// normalised tables of one chain level (h = N/2 entries each); f_top strided by fstride is the level's f
+void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
+void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st);
+void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st);  // out[i] = a[i]*b[b_off + i*b_stride]
 }  // namespace k
 
 // ---- engine.cu: the algorithms on device buffers ------------------------------------------
@@ -164,7 +180,8 @@ struct Engine {
 // ---- builder.cu / serialize.cu --------------------------------------------------------------
 Tree* build_secp256k1(size_t n, int parts, int device);                                     // lib.rs:39-85
 Tree* tree_from_leaves(const Fp* leaves_dev_plain, size_t n, const std::vector<RatMapHost>& maps, int parts, int device);  // fftree.rs:42-70
-void finish_tree(Tree& t);                                                                  // fftree.rs:318-463 for every chain level
+void finish_tree(Tree& t);
+void build_norm_tables(Tree& t, uint32_t level);  // normalised-butterfly tables from f + rmat                                                                  // fftree.rs:318-463 for every chain level
 size_t serialized_size(const Tree& t, bool compressed);
 size_t serialize(const Tree& t, bool compressed, uint8_t* buf, size_t cap);
 Tree* deserialize(const uint8_t* buf, size_t len, bool compressed, int device);

@@ -214,6 +214,23 @@ FP_HD Fp fp_sub(const Fp& a, const Fp& b) {
 
 FP_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
 
+// a - b mod p for lazy a in [0,2^256) and CANONICAL b; lazy result in [0,2^256)
+FP_HD Fp fp_sub_lazy(const Fp& a, const Fp& b) {
+  Fp d;
+  d.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) d.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t borrow = subc(0u, 0u);
+  // a < b <= p-1: a - b + p lies in (0, p): one correction is exact
+  uint32_t m977 = borrow & FP_C977, m1 = borrow & 1u;
+  Fp r;
+  r.v[0] = sub_cc(d.v[0], m977);
+  r.v[1] = subc_cc(d.v[1], m1);
+#pragma unroll
+  for (int i = 2; i < 8; i++) r.v[i] = subc_cc(d.v[i], 0u);
+  return r;
+}
+
 // ---------------------------------------------------------------------------
 // 512(+1)-bit product accumulator, split into an even-aligned and an
 // odd-aligned half so every partial product lands on a 64-bit-aligned limb

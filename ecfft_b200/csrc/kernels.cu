@@ -10,7 +10,9 @@
 #include "ec.cuh"
 
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
+#include <string>
 
 namespace ecfft {
 
@@ -103,17 +105,21 @@ static void map(size_t n, cudaStream_t st, F f) {
 struct TileParams {
   const Fp* in;
   Fp* out;
-  const Fp* dmat;
-  const Fp* rmat;
+  const Fp* dmat;   // MODE 0: decompose matrices | MODE 1: tw_d[source] ({c, -s0} per butterfly)
+  const Fp* rmat;   // MODE 0: recombine matrices | MODE 1: tw_r[target] ({s0, s1} per butterfly)
+  const Fp* pre;    // MODE 1: per-position scale applied on load (1/Gamma^source) or null
+  const Fp* post;   // MODE 1: per-position scale applied on store (Gamma^target) or null
   unsigned long long nvec;
   unsigned long long total;  // nvec * h, guards the ragged last tile of the packed mode
   uint32_t log_h, j_lo, j_hi, log_c;
   uint32_t log_t;            // tile holds 2^log_t elements
   uint32_t packed;           // 1: h <= tile, a tile is 2^(log_t-log_h) whole consecutive vectors
+  uint32_t norm;             // 1: normalised butterflies (MODE 1)
   uint32_t do_d, do_r, skip_d, skip_r;
 };
 
-__device__ __forceinline__ void butterfly(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* m) {
+// MODE 0 — the reference's 2x2 mat-vec (src/utils.rs:338-347): 4 products, 2 lazy reductions
+__device__ __forceinline__ void butterfly_matrix(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* m) {
   Fp m0 = fp_load_ro(m), m1 = fp_load_ro(m + 1);
   Fp x0 = s[e_lo], x1 = s[e_hi];
   Fp y0 = fp_dot2_lazy(m0, x0, m1, x1);
@@ -122,12 +128,29 @@ __device__ __forceinline__ void butterfly(Fp* s, uint32_t e_lo, uint32_t e_hi, c
   Fp y1 = fp_dot2_lazy(m2, x0, m3, x1);
   s[e_hi] = y1;
 }
+// MODE 1 recombine: [[1, s0], [1, s1]] — the two outputs are x_p + s*x_q at the pair's two nodes
+__device__ __forceinline__ void butterfly_norm_r(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
+  Fp s0 = fp_load_ro(tw), s1 = fp_load_ro(tw + 1);
+  Fp xp = s[e_lo], xq = s[e_hi];
+  s[e_lo] = fp_muladd_lazy(xp, s0, xq);
+  s[e_hi] = fp_muladd_lazy(xp, s1, xq);
+}
+// MODE 1 decompose: inverse of [[1, s0], [1, s1]]: y_q = (x_q - x_p)/(s1 - s0), y_p = x_p - s0*y_q
+__device__ __forceinline__ void butterfly_norm_d(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
+  Fp c = fp_load_ro(tw), ns0 = fp_load_ro(tw + 1);
+  Fp xp = fp_canon(s[e_lo]), xq = s[e_hi];
+  Fp yq = fp_mul_lazy(c, fp_sub_lazy(xq, xp));
+  s[e_hi] = yq;
+  s[e_lo] = fp_muladd_lazy(xp, ns0, yq);
+}
 
+template <int MODE>
 __global__ void __launch_bounds__(NT, 2) k_extend_tile(TileParams p) {
   extern __shared__ uint4 smem_raw[];
   Fp* s = reinterpret_cast<Fp*>(smem_raw);
   const uint32_t T = 1u << p.log_t;
   const uint32_t C = 1u << p.log_c;
+  const unsigned long long hmask = (1ull << p.log_h) - 1;
   unsigned long long pos0, gbase;
   if (p.packed) {  // j_lo = 0, C = 1: element e of the tile is global element gbase + e
     pos0 = 0;
@@ -145,7 +168,9 @@ __global__ void __launch_bounds__(NT, 2) k_extend_tile(TileParams p) {
   for (uint32_t e = threadIdx.x; e < T; e += NT) {
     uint32_t r = e >> p.log_c, c = e & (C - 1);
     unsigned long long g = gbase + ((unsigned long long)r << p.j_lo) + c;
-    s[e] = g < p.total ? fp_load(p.in + g) : fp_zero();
+    Fp x = g < p.total ? fp_load(p.in + g) : fp_zero();
+    if (MODE == 1 && p.pre) x = fp_mul_lazy(x, fp_load_ro(p.pre + (g & hmask)));
+    s[e] = x;
   }
   __syncthreads();
 
@@ -153,12 +178,15 @@ __global__ void __launch_bounds__(NT, 2) k_extend_tile(TileParams p) {
     for (int j = (int)p.j_hi - 1; j >= (int)p.j_lo; j--) {
       const uint32_t sh = (uint32_t)j - p.j_lo + p.log_c;  // bit of the tile index that this level pairs
       const unsigned long long jmask = (1ull << j) - 1;
-      const Fp* layer = p.dmat + 4 * ((2ull << j) + p.skip_d);
+      const Fp* layer = MODE == 0 ? p.dmat + 4 * ((2ull << j) + p.skip_d) : p.dmat + 2 * (1ull << j);
       for (uint32_t b = threadIdx.x; b < T / 2; b += NT) {
         uint32_t e_lo = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
         uint32_t r = e_lo >> p.log_c, c = e_lo & (C - 1);
         unsigned long long i = (pos0 + ((unsigned long long)r << p.j_lo) + c) & jmask;
-        butterfly(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
+        if (MODE == 0)
+          butterfly_matrix(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
+        else
+          butterfly_norm_d(s, e_lo, e_lo + (1u << sh), layer + 2 * i);
       }
       __syncthreads();
     }
@@ -167,12 +195,15 @@ __global__ void __launch_bounds__(NT, 2) k_extend_tile(TileParams p) {
     for (uint32_t j = p.j_lo; j < p.j_hi; j++) {
       const uint32_t sh = j - p.j_lo + p.log_c;
       const unsigned long long jmask = (1ull << j) - 1;
-      const Fp* layer = p.rmat + 4 * ((2ull << j) + p.skip_r);
+      const Fp* layer = MODE == 0 ? p.rmat + 4 * ((2ull << j) + p.skip_r) : p.rmat + 2 * (1ull << j);
       for (uint32_t b = threadIdx.x; b < T / 2; b += NT) {
         uint32_t e_lo = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
         uint32_t r = e_lo >> p.log_c, c = e_lo & (C - 1);
         unsigned long long i = (pos0 + ((unsigned long long)r << p.j_lo) + c) & jmask;
-        butterfly(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
+        if (MODE == 0)
+          butterfly_matrix(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
+        else
+          butterfly_norm_r(s, e_lo, e_lo + (1u << sh), layer + 2 * i);
       }
       __syncthreads();
     }
@@ -180,14 +211,19 @@ __global__ void __launch_bounds__(NT, 2) k_extend_tile(TileParams p) {
   for (uint32_t e = threadIdx.x; e < T; e += NT) {
     uint32_t r = e >> p.log_c, c = e & (C - 1);
     unsigned long long g = gbase + ((unsigned long long)r << p.j_lo) + c;
-    if (g < p.total) fp_store(p.out + g, fp_canon(s[e]));
+    if (g < p.total) {
+      Fp x = s[e];
+      if (MODE == 1 && p.post) x = fp_mul_lazy(x, fp_load_ro(p.post + (g & hmask)));
+      fp_store(p.out + g, fp_canon(x));
+    }
   }
 }
 
 static void launch_tile(const TileParams& p, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << LOG_TILE) * sizeof(Fp))));
+    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << LOG_TILE) * sizeof(Fp))));
+    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << LOG_TILE) * sizeof(Fp))));
     configured = true;
   }
   size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
@@ -201,21 +237,41 @@ static void launch_tile(const TileParams& p, cudaStream_t st) {
     for (uint32_t j = p.j_lo; j < p.j_hi; j++) mats += (double)(p.do_d + p.do_r) * 128.0 * (double)(1ull << j);
     prof::record_begin(prof::EXTEND_TILE, levels * 64.0 * (double)p.total + mats, st);
   }
-  k_extend_tile<<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
+  if (p.norm)
+    k_extend_tile<1><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
+  else
+    k_extend_tile<0><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
   if (timed) prof::record_end(st);
   prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 
-void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st) {
+int butterfly_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ECFFT_B200_BUTTERFLY");
+    mode = (e && std::string(e) == "matrix") ? 0 : 1;
+  }
+  return mode;
+}
+
+void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st, bool unscaled_out) {
   if (nvec == 0) return;
   if (log_h == 0) {  // extend_impl n == 1: identity, fftree.rs:74-76
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, nvec * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
   }
   TileParams p;
-  p.dmat = lv.dmat;
-  p.rmat = lv.rmat;
+  const Moiety source = target == S1 ? S0 : S1;
+  const bool norm = butterfly_mode() == 1 && lv.tw_r[target] && lv.tw_d[source] && lv.gam[target] && lv.gami[source];
+  if (unscaled_out && !norm) throw Error(ERR_INVALID_ARG, "extend: unscaled output needs the normalised tables");
+  p.norm = norm ? 1 : 0;
+  p.dmat = norm ? lv.tw_d[source] : lv.dmat;
+  p.rmat = norm ? lv.tw_r[target] : lv.rmat;
+  const Fp* pre = norm ? lv.gami[source] : nullptr;
+  const Fp* post = (norm && !unscaled_out) ? lv.gam[target] : nullptr;
+  p.pre = nullptr;
+  p.post = nullptr;
   p.nvec = nvec;
   p.total = nvec << log_h;
   p.log_h = log_h;
@@ -230,6 +286,8 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
     p.packed = 1;
     p.log_t = log_h;
     while (p.log_t < LOG_TILE && ((size_t)1 << p.log_t) < p.total) p.log_t++;
+    p.pre = pre;
+    p.post = post;
     launch_tile(p, st);
     return;
   }
@@ -245,25 +303,32 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
     p.in = src; p.out = out;
     p.j_hi = bounds[i]; p.j_lo = bounds[i + 1]; p.log_c = LOG_TILE - (p.j_hi - p.j_lo);
     p.do_d = 1; p.do_r = 0;
+    p.pre = i == 0 ? pre : nullptr;  // 1/Gamma^source on the very first load
     launch_tile(p, st);
     src = out;
   }
+  p.pre = nullptr;
   p.in = out; p.out = out; p.j_lo = 0; p.j_hi = LOG_TILE; p.log_c = 0; p.do_d = 1; p.do_r = 1;
   launch_tile(p, st);
   for (uint32_t i = npass; i-- > 0;) {
     p.in = out; p.out = out;
     p.j_hi = bounds[i]; p.j_lo = bounds[i + 1]; p.log_c = LOG_TILE - (p.j_hi - p.j_lo);
     p.do_d = 0; p.do_r = 1;
+    p.post = i == 0 ? post : nullptr;  // Gamma^target on the very last store
     launch_tile(p, st);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // ENTER combine: res[2i] = u0[i] + v0[i]*xnn[2i], res[2i+1] = u1[i] + v1[i]*xnn[2i+1]
-// A holds [u0 | v0] per block of 2h, W holds [u1 | v1].
+// A holds [u0 | v0] per block of 2h, W holds [u1 | v1].  SCALED: W lacks the Gamma^1 scaling of the
+// normalised EXTEND, so res[2i+1] = gam[i]*u1^[i] + (gam[i]*xnn[2i+1])*v1^[i] with both constants
+// precomputed (one lazy reduction for the two products).
 // ------------------------------------------------------------------------------------------
+template <bool SCALED>
 __global__ void __launch_bounds__(256) k_enter_combine(const Fp* __restrict__ A, const Fp* __restrict__ W,
-                                                       const Fp* __restrict__ xnn, Fp* __restrict__ out,
+                                                       const Fp* __restrict__ xnn, const Fp* __restrict__ gam,
+                                                       const Fp* __restrict__ gx, Fp* __restrict__ out,
                                                        uint32_t log_h, unsigned long long npairs) {
   for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs;
        idx += (unsigned long long)gridDim.x * blockDim.x) {
@@ -275,18 +340,26 @@ __global__ void __launch_bounds__(256) k_enter_combine(const Fp* __restrict__ A,
     Fp r0 = fp_canon(fp_muladd_lazy(u0, v0, x0));
     fp_store(out + off + 2 * i, r0);
     Fp u1 = fp_load(W + off + i), v1 = fp_load(W + off + h + i);
-    Fp x1 = fp_load_ro(xnn + 2 * i + 1);
-    Fp r1 = fp_canon(fp_muladd_lazy(u1, v1, x1));
+    Fp r1;
+    if (SCALED) {
+      r1 = fp_canon(fp_dot2_lazy(fp_load_ro(gam + i), u1, fp_load_ro(gx + i), v1));
+    } else {
+      Fp x1 = fp_load_ro(xnn + 2 * i + 1);
+      r1 = fp_canon(fp_muladd_lazy(u1, v1, x1));
+    }
     fp_store(out + off + 2 * i + 1, r1);
   }
 }
-void enter_combine(const Fp* A, const Fp* W, const Fp* xnn, Fp* out, uint32_t log_h, size_t n, cudaStream_t st) {
+void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t log_h, size_t n, bool W_unscaled, cudaStream_t st) {
   size_t npairs = n / 2;
   unsigned grid = (unsigned)((npairs + 255) / 256);
   if (grid > 148u * 32u) grid = 148u * 32u;
   const bool timed = prof::enabled();
   if (timed) prof::record_begin(prof::ENTER_COMBINE, 128.0 * (double)n, st);  // u0,v0,u1,v1 / xnn / out
-  k_enter_combine<<<grid, 256, 0, st>>>(A, W, xnn, out, log_h, npairs);
+  if (W_unscaled)
+    k_enter_combine<true><<<grid, 256, 0, st>>>(A, W, lv.xnn_s, lv.gam[1], lv.gx, out, log_h, npairs);
+  else
+    k_enter_combine<false><<<grid, 256, 0, st>>>(A, W, lv.xnn_s, nullptr, nullptr, out, log_h, npairs);
   if (timed) prof::record_end(st);
   prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
@@ -538,6 +611,42 @@ void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, 
     fp_store(m + 2, fp_mul(fp_neg(r2), di));
     fp_store(m + 3, fp_mul(r0, di));
   });
+}
+
+// Normalised-butterfly tables of one chain level (DESIGN.md "twiddle form").  Entry idx = 2^j + i:
+// s0 = f[2B + 2i + mu], s1 = f[2B + 2i + mu + B] with B = 2^(j+1) — the same nodes the reference's
+// matrices are built from (src/fftree.rs:356-357) — through the strided view of the top tree's f.
+void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t idx) {
+    if (idx == 0) {
+      fp_store(tw_r, fp_zero()); fp_store(tw_r + 1, fp_zero());
+      fp_store(tw_d, fp_zero()); fp_store(tw_d + 1, fp_zero());
+      return;
+    }
+    uint32_t j = 63 - __clzll((unsigned long long)idx);
+    size_t i = idx - ((size_t)1 << j), B = (size_t)2 << j;
+    Fp s0 = fp_load(f_top + (2 * B + 2 * i + mu) * fstride);
+    Fp s1 = fp_load(f_top + (2 * B + 2 * i + mu + B) * fstride);
+    fp_store(tw_r + 2 * idx, s0);
+    fp_store(tw_r + 2 * idx + 1, s1);
+    fp_store(tw_d + 2 * idx, fp_inv(fp_sub(s1, s0)));
+    fp_store(tw_d + 2 * idx + 1, fp_neg(s0));
+  });
+}
+// Gamma^mu_p = prod_j v(node_j(p))^(2^j - 1): exactly the first-column entries of the recombine
+// matrices the position passes through (R = [[v0, s0 v0], [v1, s1 v1]], src/fftree.rs:360)
+void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t p) {
+    Fp acc = fp_one();
+    for (uint32_t j = 0; ((size_t)1 << j) < h; j++) {
+      size_t i = p & (((size_t)1 << j) - 1), b = (p >> j) & 1;
+      acc = fp_mul_lazy(acc, fp_load(rmat + 4 * (((size_t)2 << j) + 2 * i + mu) + 2 * b));
+    }
+    fp_store(gam + p, fp_canon(acc));
+  });
+}
+void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st) {
+  map(n, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_load(a + i), fp_load(b + b_off + i * b_stride))); });
 }
 
 }  // namespace k

@@ -224,6 +224,8 @@ Tree* deserialize(const uint8_t* buf, size_t len, bool compressed, int device) {
     ECFFT_CUDA(cudaMemcpyAsync(&nbad, bad, sizeof nbad, cudaMemcpyDeviceToHost, t->stream));
     ECFFT_CUDA(cudaStreamSynchronize(t->stream));
     if (nbad) throw Error(ERR_BAD_BYTES, "deserialize: element >= p");
+    for (uint32_t lvl = 1; lvl <= t->log_n; lvl++) build_norm_tables(*t, lvl);
+    ECFFT_CUDA(cudaStreamSynchronize(t->stream));
     const size_t n = t->n();
     t->base_leaf0 = fp_zero();
     t->base_leaf1 = fp_zero();

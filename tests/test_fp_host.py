@@ -72,6 +72,9 @@ def test_add_sub_mont(shim):
         assert dec(out) == (a + b) % P
         shim.fph_sub(enc(a), enc(b), out)
         assert dec(out) == (a - b) % P
+        lazy = rnd(r)                                # any 256-bit pattern minus a canonical value
+        shim.fph_sub_lazy(enc(lazy), enc(b), out)
+        assert dec(out) % P == (lazy - b) % P
         shim.fph_mont_mul(enc(a), enc(b), out)      # the CIOS Montgomery alternative (a*b*R^-1)
         assert dec(out) == a * b * rinv % P
 

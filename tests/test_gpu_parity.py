@@ -215,3 +215,25 @@ def test_tree_new_from_leaves(oracle_mod):
     t = ecfft_b200.FFTree.new(leaves, maps)
     for name in TABLES:
         eq(t.table(name), ref.table(ORACLE_NAMES.get(name, name)))
+
+
+def test_matrix_butterfly_mode_matches_too():
+    """ECFFT_B200_BUTTERFLY=matrix selects the reference-shaped 2x2 mat-vec butterflies (the measured
+    'phase 1' kernel); both modes must give the oracle's bits."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, ecfft_b200\n"
+        "from oracle import oracle as O\n"
+        "n = 1 << 13\n"
+        "g = ecfft_b200.build_fftree(n); c = O.OracleTree.build(n)\n"
+        "x = O.random_elements(n, seed=3)\n"
+        "assert (g.enter(x) == c.enter(x)).all()\n"
+        "assert (g.exit(x) == c.exit(x)).all()\n"
+        "assert (g.extend(x[:n//2], 0) == c.extend(x[:n//2], 0)).all()\n"
+        "print('matrix mode ok')\n")
+    env = dict(os.environ, ECFFT_B200_BUTTERFLY="matrix")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "matrix mode ok" in r.stdout, r.stdout + r.stderr

@@ -22,3 +22,4 @@ void fph_pow(const uint32_t* a, uint64_t e, uint32_t* r) { Fp x; memcpy(&x, a, 3
 void fph_consts(uint32_t* R, uint32_t* RINV) { Fp a = fp_const_R(), b = fp_const_RINV(); memcpy(R, &a, 32); memcpy(RINV, &b, 32); }
 }
 extern "C" void fph_sqrt(const uint32_t* a, uint32_t* r) { Fp x; memcpy(&x, a, 32); Fp z = fp_sqrt_candidate(x); memcpy(r, &z, 32); }
+extern "C" void fph_sub_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_sub_lazy(x, y); memcpy(r, &z, 32); }
