@@ -66,9 +66,6 @@ void read(Kernel k, double* ms, double* alg_bytes, unsigned long long* n) {
 
 namespace k {
 
-static constexpr int NT = 256;              // threads per CTA for the tile kernel
-static constexpr uint32_t LOG_TILE = 11;    // 2048 elements = 64 KiB of shared memory per CTA
-
 static inline unsigned grid_for(size_t n, int threads) {
   size_t g = (n + threads - 1) / threads;
   size_t cap = 148u * 64u;  // grid-stride beyond this
@@ -87,236 +84,6 @@ static void map(size_t n, cudaStream_t st, F f) {
   k_map<<<grid_for(n, 256), 256, 0, st>>>(n, f);
   prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
-}
-
-// ------------------------------------------------------------------------------------------
-// EXTEND tile kernel.
-//
-// A vector of length h is viewed through the levels of the butterfly network: the level with
-// half-stride 2^j pairs positions p and p + 2^j (bit j of p clear) and uses matrix
-// M[2^(j+1) + 2*(p mod 2^j) + skip] of the chain level's matrix BinaryTree (layer offset =
-// block size, reference src/utils.rs:248-252).  A CTA owns every element that agrees on all
-// position bits outside [j_lo, j_hi) and on the high column bits: 2^(j_hi-j_lo) rows of
-// C = 2^log_c contiguous elements.  It runs the decompose levels j = j_hi-1 .. j_lo, then (for
-// the innermost pass) the recombine levels j = j_lo .. j_hi-1, with one __syncthreads() per
-// level and no global traffic in between.  Blocks are ordered batch-major so CTAs resident at
-// the same time share matrix lines in L2/L1.
-// ------------------------------------------------------------------------------------------
-struct TileParams {
-  const Fp* in;
-  Fp* out;
-  const Fp* dmat;   // MODE 0: decompose matrices | MODE 1: tw_d[source] ({c, -s0} per butterfly)
-  const Fp* rmat;   // MODE 0: recombine matrices | MODE 1: tw_r[target] ({s0, s1} per butterfly)
-  const Fp* pre;    // MODE 1: per-position scale applied on load (1/Gamma^source) or null
-  const Fp* post;   // MODE 1: per-position scale applied on store (Gamma^target) or null
-  unsigned long long nvec;
-  unsigned long long total;  // nvec * h, guards the ragged last tile of the packed mode
-  uint32_t log_h, j_lo, j_hi, log_c;
-  uint32_t log_t;            // tile holds 2^log_t elements
-  uint32_t packed;           // 1: h <= tile, a tile is 2^(log_t-log_h) whole consecutive vectors
-  uint32_t norm;             // 1: normalised butterflies (MODE 1)
-  uint32_t do_d, do_r, skip_d, skip_r;
-};
-
-// MODE 0 — the reference's 2x2 mat-vec (src/utils.rs:338-347): 4 products, 2 lazy reductions
-__device__ __forceinline__ void butterfly_matrix(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* m) {
-  Fp m0 = fp_load_ro(m), m1 = fp_load_ro(m + 1);
-  Fp x0 = s[e_lo], x1 = s[e_hi];
-  Fp y0 = fp_dot2_lazy(m0, x0, m1, x1);
-  Fp m2 = fp_load_ro(m + 2), m3 = fp_load_ro(m + 3);
-  s[e_lo] = y0;
-  Fp y1 = fp_dot2_lazy(m2, x0, m3, x1);
-  s[e_hi] = y1;
-}
-// MODE 1 recombine: [[1, s0], [1, s1]] — the two outputs are x_p + s*x_q at the pair's two nodes
-__device__ __forceinline__ void butterfly_norm_r(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
-  Fp s0 = fp_load_ro(tw), s1 = fp_load_ro(tw + 1);
-  Fp xp = s[e_lo], xq = s[e_hi];
-  s[e_lo] = fp_muladd_lazy(xp, s0, xq);
-  s[e_hi] = fp_muladd_lazy(xp, s1, xq);
-}
-// MODE 1 decompose: inverse of [[1, s0], [1, s1]]: y_q = (x_q - x_p)/(s1 - s0), y_p = x_p - s0*y_q
-__device__ __forceinline__ void butterfly_norm_d(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
-  Fp c = fp_load_ro(tw), ns0 = fp_load_ro(tw + 1);
-  Fp xp = fp_canon(s[e_lo]), xq = s[e_hi];
-  Fp yq = fp_mul_lazy(c, fp_sub_lazy(xq, xp));
-  s[e_hi] = yq;
-  s[e_lo] = fp_muladd_lazy(xp, ns0, yq);
-}
-
-template <int MODE>
-__global__ void __launch_bounds__(NT, 2) k_extend_tile(TileParams p) {
-  extern __shared__ uint4 smem_raw[];
-  Fp* s = reinterpret_cast<Fp*>(smem_raw);
-  const uint32_t T = 1u << p.log_t;
-  const uint32_t C = 1u << p.log_c;
-  const unsigned long long hmask = (1ull << p.log_h) - 1;
-  unsigned long long pos0, gbase;
-  if (p.packed) {  // j_lo = 0, C = 1: element e of the tile is global element gbase + e
-    pos0 = 0;
-    gbase = (unsigned long long)blockIdx.x << p.log_t;
-  } else {
-    const unsigned long long v = blockIdx.x % p.nvec;
-    const unsigned long long tile = blockIdx.x / p.nvec;
-    const uint32_t ncg_log = p.j_lo - p.log_c;
-    const unsigned long long cg = tile & ((1ull << ncg_log) - 1);
-    const unsigned long long q_hi = tile >> ncg_log;
-    pos0 = (q_hi << p.j_hi) + (cg << p.log_c);  // position within the vector of tile element 0
-    gbase = (v << p.log_h) + pos0;
-  }
-
-  for (uint32_t e = threadIdx.x; e < T; e += NT) {
-    uint32_t r = e >> p.log_c, c = e & (C - 1);
-    unsigned long long g = gbase + ((unsigned long long)r << p.j_lo) + c;
-    Fp x = g < p.total ? fp_load(p.in + g) : fp_zero();
-    if (MODE == 1 && p.pre) x = fp_mul_lazy(x, fp_load_ro(p.pre + (g & hmask)));
-    s[e] = x;
-  }
-  __syncthreads();
-
-  if (p.do_d) {
-    for (int j = (int)p.j_hi - 1; j >= (int)p.j_lo; j--) {
-      const uint32_t sh = (uint32_t)j - p.j_lo + p.log_c;  // bit of the tile index that this level pairs
-      const unsigned long long jmask = (1ull << j) - 1;
-      const Fp* layer = MODE == 0 ? p.dmat + 4 * ((2ull << j) + p.skip_d) : p.dmat + 2 * (1ull << j);
-      for (uint32_t b = threadIdx.x; b < T / 2; b += NT) {
-        uint32_t e_lo = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
-        uint32_t r = e_lo >> p.log_c, c = e_lo & (C - 1);
-        unsigned long long i = (pos0 + ((unsigned long long)r << p.j_lo) + c) & jmask;
-        if (MODE == 0)
-          butterfly_matrix(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
-        else
-          butterfly_norm_d(s, e_lo, e_lo + (1u << sh), layer + 2 * i);
-      }
-      __syncthreads();
-    }
-  }
-  if (p.do_r) {
-    for (uint32_t j = p.j_lo; j < p.j_hi; j++) {
-      const uint32_t sh = j - p.j_lo + p.log_c;
-      const unsigned long long jmask = (1ull << j) - 1;
-      const Fp* layer = MODE == 0 ? p.rmat + 4 * ((2ull << j) + p.skip_r) : p.rmat + 2 * (1ull << j);
-      for (uint32_t b = threadIdx.x; b < T / 2; b += NT) {
-        uint32_t e_lo = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
-        uint32_t r = e_lo >> p.log_c, c = e_lo & (C - 1);
-        unsigned long long i = (pos0 + ((unsigned long long)r << p.j_lo) + c) & jmask;
-        if (MODE == 0)
-          butterfly_matrix(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
-        else
-          butterfly_norm_r(s, e_lo, e_lo + (1u << sh), layer + 2 * i);
-      }
-      __syncthreads();
-    }
-  }
-  for (uint32_t e = threadIdx.x; e < T; e += NT) {
-    uint32_t r = e >> p.log_c, c = e & (C - 1);
-    unsigned long long g = gbase + ((unsigned long long)r << p.j_lo) + c;
-    if (g < p.total) {
-      Fp x = s[e];
-      if (MODE == 1 && p.post) x = fp_mul_lazy(x, fp_load_ro(p.post + (g & hmask)));
-      fp_store(p.out + g, fp_canon(x));
-    }
-  }
-}
-
-static void launch_tile(const TileParams& p, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << LOG_TILE) * sizeof(Fp))));
-    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << LOG_TILE) * sizeof(Fp))));
-    configured = true;
-  }
-  size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
-  if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
-  const bool timed = prof::enabled();
-  if (timed) {
-    // algorithmic bytes: every fused level reads and writes each element once (64 B) and reads its
-    // 2^j matrices (128 B each) once
-    double levels = (double)(p.j_hi - p.j_lo) * (p.do_d + p.do_r);
-    double mats = 0;
-    for (uint32_t j = p.j_lo; j < p.j_hi; j++) mats += (double)(p.do_d + p.do_r) * 128.0 * (double)(1ull << j);
-    prof::record_begin(prof::EXTEND_TILE, levels * 64.0 * (double)p.total + mats, st);
-  }
-  if (p.norm)
-    k_extend_tile<1><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
-  else
-    k_extend_tile<0><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
-  if (timed) prof::record_end(st);
-  prof::count_launch();
-  ECFFT_CUDA(cudaGetLastError());
-}
-
-int butterfly_mode() {
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("ECFFT_B200_BUTTERFLY");
-    mode = (e && std::string(e) == "matrix") ? 0 : 1;
-  }
-  return mode;
-}
-
-void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st, bool unscaled_out) {
-  if (nvec == 0) return;
-  if (log_h == 0) {  // extend_impl n == 1: identity, fftree.rs:74-76
-    if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, nvec * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
-    return;
-  }
-  TileParams p;
-  const Moiety source = target == S1 ? S0 : S1;
-  const bool norm = butterfly_mode() == 1 && lv.tw_r[target] && lv.tw_d[source] && lv.gam[target] && lv.gami[source];
-  if (unscaled_out && !norm) throw Error(ERR_INVALID_ARG, "extend: unscaled output needs the normalised tables");
-  p.norm = norm ? 1 : 0;
-  p.dmat = norm ? lv.tw_d[source] : lv.dmat;
-  p.rmat = norm ? lv.tw_r[target] : lv.rmat;
-  const Fp* pre = norm ? lv.gami[source] : nullptr;
-  const Fp* post = (norm && !unscaled_out) ? lv.gam[target] : nullptr;
-  p.pre = nullptr;
-  p.post = nullptr;
-  p.nvec = nvec;
-  p.total = nvec << log_h;
-  p.log_h = log_h;
-  p.log_t = LOG_TILE;
-  p.packed = 0;
-  p.skip_d = target == S0 ? 1 : 0;  // fftree.rs:87-90
-  p.skip_r = target == S1 ? 1 : 0;  // fftree.rs:108-111
-  if (log_h <= LOG_TILE) {
-    // whole vectors fit a tile: pack 2^(log_t-log_h) consecutive vectors per CTA
-    p.in = in; p.out = out;
-    p.j_lo = 0; p.j_hi = log_h; p.log_c = 0; p.do_d = 1; p.do_r = 1;
-    p.packed = 1;
-    p.log_t = log_h;
-    while (p.log_t < LOG_TILE && ((size_t)1 << p.log_t) < p.total) p.log_t++;
-    p.pre = pre;
-    p.post = post;
-    launch_tile(p, st);
-    return;
-  }
-  // outer decompose passes (strided tiles), inner fused pass, outer recombine passes
-  const uint32_t outer = log_h - LOG_TILE;
-  const uint32_t kmax = 6;                        // 64 rows x 32 columns (1 KiB contiguous per row)
-  const uint32_t npass = (outer + kmax - 1) / kmax;
-  std::vector<uint32_t> bounds;                   // j boundaries from log_h down to LOG_TILE
-  bounds.push_back(log_h);
-  for (uint32_t i = 1; i <= npass; i++) bounds.push_back(log_h - (outer * i) / npass);
-  const Fp* src = in;
-  for (uint32_t i = 0; i < npass; i++) {
-    p.in = src; p.out = out;
-    p.j_hi = bounds[i]; p.j_lo = bounds[i + 1]; p.log_c = LOG_TILE - (p.j_hi - p.j_lo);
-    p.do_d = 1; p.do_r = 0;
-    p.pre = i == 0 ? pre : nullptr;  // 1/Gamma^source on the very first load
-    launch_tile(p, st);
-    src = out;
-  }
-  p.pre = nullptr;
-  p.in = out; p.out = out; p.j_lo = 0; p.j_hi = LOG_TILE; p.log_c = 0; p.do_d = 1; p.do_r = 1;
-  launch_tile(p, st);
-  for (uint32_t i = npass; i-- > 0;) {
-    p.in = out; p.out = out;
-    p.j_hi = bounds[i]; p.j_lo = bounds[i + 1]; p.log_c = LOG_TILE - (p.j_hi - p.j_lo);
-    p.do_d = 0; p.do_r = 1;
-    p.post = i == 0 ? post : nullptr;  // Gamma^target on the very last store
-    launch_tile(p, st);
-  }
 }
 
 // ------------------------------------------------------------------------------------------
