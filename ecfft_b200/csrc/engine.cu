@@ -2,6 +2,8 @@
 // device kernels.  The reference recurses on Vec<F>; here every recursion depth is one batched
 // launch over all sub-problems of that depth (they share the chain level's tables):
 //   ENTER / VANISH run bottom-up, EXIT runs top-down, DEGREE follows its single branch.
+#include <cstdlib>
+
 #include "engine.h"
 
 namespace ecfft {
@@ -62,6 +64,19 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
   Fp* ping[2] = {nullptr, nullptr};
   const Fp* cur = in;
   uint32_t idx = 0;
+  // depths with block size <= 1024 run fused in shared memory (k_enter_small)
+  if (m_lo < 1024 && !getenv("ECFFT_B200_NO_SMALL_FUSION")) {
+    const size_t m_small = m_hi < 1024 ? m_hi : 1024;
+    Fp* dst = (m_small == m_hi && out != in) ? out : (ping[0] = tmp(n));
+    if (k::enter_small(t.levels.data(), cur, dst, n, m_lo, m_small, st)) {
+      cur = dst;
+      m_lo = m_small;
+      idx = 1;
+    } else if (ping[0]) {
+      release(ping[0]);
+      ping[0] = nullptr;
+    }
+  }
   for (size_t m = m_lo * 2; m <= m_hi; m *= 2, idx++) {
     const Level& lv = level_for(m);
     const size_t h = m / 2;

@@ -110,6 +110,8 @@ namespace k {
 // the final Gamma scaling to the caller (ENTER folds it into its combine).
 void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st,
             bool unscaled_out = false);
+// all ENTER depths m_lo < m <= m_hi <= 1024 in one shared-memory kernel; false if unavailable
+bool enter_small(const Level* levels, const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, cudaStream_t st);
 int butterfly_mode();  // 1 = normalised (default), 0 = 2x2 matrices (ECFFT_B200_BUTTERFLY=matrix)
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
 // scaling (lv.gam[1], lv.gx are used instead of xnn's odd entries).

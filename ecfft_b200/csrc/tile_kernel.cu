@@ -268,5 +268,121 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// k_enter_small: every ENTER recursion depth with block size m <= 2^LOG_SMALL in ONE launch.
+// A CTA owns 2^log_t consecutive coefficients; per depth it (1) copies the current vectors scaled by
+// 1/Gamma^0 into a work buffer, (2) runs the normalised decompose + recombine levels of EXTEND -> S1 on
+// it, (3) combines (src/fftree.rs:155-159) into a third buffer — all in shared memory.  Replaces
+// 2 launches and ~160 B/element of HBM traffic per depth of the generic path.
+// ------------------------------------------------------------------------------------------
+static constexpr uint32_t LOG_SMALL = 10;  // 3 buffers x 1024 x 32 B = 96 KiB per CTA, 2 CTAs/SM
+struct SmallLevel {
+  const Fp* tw_d0;   // level's tw_d[0]
+  const Fp* tw_r1;   // tw_r[1]
+  const Fp* gami0;
+  const Fp* gam1;
+  const Fp* gx;
+  const Fp* xnn;
+};
+struct SmallParams {
+  const Fp* in;
+  Fp* out;
+  unsigned long long total;
+  uint32_t log_t;           // tile size (<= LOG_SMALL)
+  uint32_t lvl_lo, lvl_hi;  // depths with log2(m) in (lvl_lo, lvl_hi]
+  SmallLevel lv[LOG_SMALL + 1];  // indexed by log2(m)
+};
+
+__global__ void __launch_bounds__(256, 2) k_enter_small(const __grid_constant__ SmallParams p) {
+  extern __shared__ uint4 smem_raw[];
+  const uint32_t T = 1u << p.log_t;
+  Fp* A = reinterpret_cast<Fp*>(smem_raw);
+  Fp* W = A + T;
+  Fp* B = W + T;
+  const unsigned long long gbase = (unsigned long long)blockIdx.x << p.log_t;
+  for (uint32_t e = threadIdx.x; e < T; e += 256) A[e] = gbase + e < p.total ? fp_load(p.in + gbase + e) : fp_zero();
+  __syncthreads();
+  for (uint32_t lm = p.lvl_lo + 1; lm <= p.lvl_hi; lm++) {
+    const SmallLevel& lv = p.lv[lm];
+    const uint32_t L = lm - 1, h = 1u << L;
+    if (L > 0) {
+      for (uint32_t e = threadIdx.x; e < T; e += 256) W[e] = fp_mul_lazy(A[e], fp_load_ro(lv.gami0 + (e & (h - 1))));
+      __syncthreads();
+      for (int j = (int)L - 1; j >= 0; j--) {
+        const Fp* layer = lv.tw_d0 + 2 * (1u << j);
+#pragma unroll 1
+        for (uint32_t b = threadIdx.x; b < T / 2; b += 256) {
+          uint32_t e_lo = ((b >> j) << (j + 1)) | (b & ((1u << j) - 1));
+          butterfly_norm_d(W, e_lo, e_lo + (1u << j), layer + 2 * (e_lo & ((1u << j) - 1)));
+        }
+        __syncthreads();
+      }
+      for (uint32_t j = 0; j < L; j++) {
+        const Fp* layer = lv.tw_r1 + 2 * (1u << j);
+#pragma unroll 1
+        for (uint32_t b = threadIdx.x; b < T / 2; b += 256) {
+          uint32_t e_lo = ((b >> j) << (j + 1)) | (b & ((1u << j) - 1));
+          butterfly_norm_r(W, e_lo, e_lo + (1u << j), layer + 2 * (e_lo & ((1u << j) - 1)));
+        }
+        __syncthreads();
+      }
+    }
+    const Fp* Wsrc = L > 0 ? W : A;  // EXTEND of a length-1 vector is the identity (fftree.rs:74-76)
+#pragma unroll 1
+    for (uint32_t idx = threadIdx.x; idx < T / 2; idx += 256) {
+      uint32_t blk = idx >> L, i = idx & (h - 1), off = blk << lm;
+      Fp u0 = A[off + i], v0 = A[off + h + i];
+      B[off + 2 * i] = fp_muladd_lazy(u0, v0, fp_load_ro(lv.xnn + 2 * i));
+      Fp u1 = Wsrc[off + i], v1 = Wsrc[off + h + i];
+      B[off + 2 * i + 1] = fp_dot2_lazy(fp_load_ro(lv.gam1 + i), u1, fp_load_ro(lv.gx + i), v1);
+    }
+    __syncthreads();
+    Fp* sw = A; A = B; B = sw;
+  }
+  for (uint32_t e = threadIdx.x; e < T; e += 256)
+    if (gbase + e < p.total) fp_store(p.out + gbase + e, fp_canon(A[e]));
+}
+
+// runs depths m_lo < m <= m_hi (m_hi <= 2^LOG_SMALL, m_hi <= n) of the bottom-up ENTER; levels[k] is the
+// chain level with 2^k leaves.  Returns false when the normalised tables are not available.
+bool enter_small(const Level* levels, const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, cudaStream_t st) {
+  if (butterfly_mode() != 1) return false;
+  uint32_t lo = 0, hi = 0;
+  while (((size_t)1 << lo) < m_lo) lo++;
+  while (((size_t)1 << hi) < m_hi) hi++;
+  if (hi > LOG_SMALL || hi <= lo) return false;
+  SmallParams p;
+  p.in = in;
+  p.out = out;
+  p.total = n;
+  p.log_t = hi;  // a tile must hold whole blocks of the largest depth
+  while (p.log_t < LOG_SMALL && ((size_t)1 << p.log_t) < n) p.log_t++;
+  p.lvl_lo = lo;
+  p.lvl_hi = hi;
+  for (uint32_t k = lo + 1; k <= hi; k++) {
+    const Level& lv = levels[k];
+    if (!lv.tw_d[0] || !lv.tw_r[1] || !lv.gami[0] || !lv.gam[1] || !lv.gx) return false;
+    p.lv[k] = SmallLevel{lv.tw_d[0], lv.tw_r[1], lv.gami[0], lv.gam[1], lv.gx, lv.xnn_s};
+  }
+  static bool configured = false;
+  if (!configured) {
+    ECFFT_CUDA(cudaFuncSetAttribute(k_enter_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(3 * (1u << LOG_SMALL) * sizeof(Fp))));
+    configured = true;
+  }
+  size_t tiles = (n + ((size_t)1 << p.log_t) - 1) >> p.log_t;
+  const bool timed = prof::enabled();
+  if (timed) {
+    // algorithmic bytes of the depths covered: level passes 64 B/elem each + combines 128 B/elem each
+    double bytes = 0;
+    for (uint32_t k = lo + 1; k <= hi; k++) bytes += (double)n * (64.0 * 2 * (k - 1) + 128.0);
+    prof::record_begin(prof::EXTEND_TILE, bytes, st);
+  }
+  k_enter_small<<<(unsigned)tiles, 256, 3 * (((size_t)sizeof(Fp)) << p.log_t), st>>>(p);
+  if (timed) prof::record_end(st);
+  prof::count_launch();
+  ECFFT_CUDA(cudaGetLastError());
+  return true;
+}
+
 }  // namespace k
 }  // namespace ecfft

@@ -237,3 +237,76 @@ def test_matrix_butterfly_mode_matches_too():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "matrix mode ok" in r.stdout, r.stdout + r.stderr
+
+
+# ---- BASELINE.json full sizes: size-independent properties (the oracle needs minutes there) ----
+@pytest.fixture(scope="module")
+def tree22():
+    import ecfft_b200
+    return ecfft_b200.build_fftree(1 << 22)          # full tree: every table of every chain level
+
+
+def _to_ints(a):
+    return [r[0] | (r[1] << 64) | (r[2] << 128) | (r[3] << 192) for r in np.asarray(a, dtype=np.uint64).tolist()]
+
+
+def test_full_size_enter_spot_checks_and_round_trip(tree22, oracle_mod):
+    """ENTER n=2^22 (BASELINE configs[2]): Horner at sampled leaves with Python big ints, linearity,
+    EXIT(ENTER(c)) == c, and the low-degree input cross-checked against the oracle on the subtree."""
+    from oracle import pyref
+    P, R = pyref.P, 2**256 % pyref.P
+    n = 1 << 22
+    c = oracle_mod.random_elements(n, seed=22)
+    ev = tree22.enter(c)
+    # (1) Horner at three leaves (values are Montgomery limbs: v~ = v*R)
+    leaves = tree22.eval_domain()
+    rinv = pow(R, -1, P)
+    coeffs = [v * rinv % P for v in _to_ints(c)]
+    for idx in (0, 1234567, n - 1):
+        x = _to_ints(leaves[idx:idx + 1])[0] * rinv % P
+        want = pyref.horner(coeffs, x)
+        assert _to_ints(ev[idx:idx + 1])[0] * rinv % P == want
+    # (2) linearity on a sample: enter(c + d) == enter(c) + enter(d)
+    d = oracle_mod.random_elements(n, seed=23)
+    cd = np.array([[(s >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)] for s in
+                   [(a + b) % P for a, b in zip(_to_ints(c[:4096]), _to_ints(d[:4096]))]], dtype=np.uint64)
+    c2 = c.copy()
+    c2[4096:] = 0
+    d2 = d.copy()
+    d2[4096:] = 0
+    cd_full = np.zeros_like(c)
+    cd_full[:4096] = cd
+    e1, e2, e3 = tree22.enter(c2), tree22.enter(d2), tree22.enter(cd_full)
+    sample = np.random.default_rng(1).integers(0, n, 2000)
+    for i in sample.tolist():
+        a, b, s = (_to_ints(t[i:i + 1])[0] for t in (e1, e2, e3))
+        assert (a + b) % P == s
+    # (3) round trip through EXIT at full size
+    eq(tree22.exit(ev), c)
+    # (4) degree < 2^14 input: its evaluations on the 2^14-leaf subtree's domain come from the oracle
+    small = oracle_mod.OracleTree.build(1 << 14, parts=1)
+    c14 = oracle_mod.random_elements(1 << 14, seed=24)
+    padded = np.zeros_like(c)
+    padded[: 1 << 14] = c14
+    big = tree22.enter(padded)
+    eq(big[:: 1 << 8], small.enter(c14))            # subtree leaves = every 2^8-th leaf (src/fftree.rs:465-482)
+
+
+def test_full_size_extend_redc_mod(tree22, oracle_mod):
+    """EXTEND n=2^20 (configs[1]) and REDC+MOD n=2^20 (configs[4]) through their defining identities"""
+    n = 1 << 20
+    c = oracle_mod.random_elements(n, seed=30)
+    ev = tree22.subtree_with_size(2 * n).enter(np.concatenate([c, np.zeros_like(c)]))   # deg < n on 2n leaves
+    eq(tree22.extend(ev[0::2], 1), ev[1::2])
+    eq(tree22.extend(ev[1::2], 0), ev[0::2])
+    # MOD by X^(n/2) with the tree's own tables keeps the low half of the coefficients (fftree.rs:206-210)
+    full = oracle_mod.random_elements(n, seed=31)
+    evn = tree22.enter(full)
+    xnn = tree22.table("xnn_s", n)
+    zz = tree22.table("z0z0_rem_xnn_s", n)
+    low = full.copy()
+    low[n // 2:] = 0
+    eq(tree22.modular_reduce(evn, xnn, zz), tree22.enter(low))
+    # REDC: h = redc_z0(P, X^(n/2)) has degree < n/2, and redc(redc(P) * c) == MOD
+    h = tree22.redc_z0(evn, xnn)
+    assert tree22.degree(h) < n // 2
