@@ -31,6 +31,7 @@ SYMBOLS = [
     "ecfft_degree_dev", "ecfft_redc_z0_dev", "ecfft_redc_z1_dev",
     "ecfft_modular_reduce_dev", "ecfft_vanish_dev", "ecfft_enter_range_dev",
     "ecfft_launch_count", "ecfft_profile_enable", "ecfft_profile_read",
+    "ecfft_mg_prescale_dev", "ecfft_mg_cross_dev", "ecfft_mg_local_dev", "ecfft_mg_combine_dev",
 ]
 
 
@@ -89,6 +90,10 @@ def load():
     L.ecfft_modular_reduce_dev.argtypes = [vp, vp, vp, vp, sz, vp, vp]
     L.ecfft_vanish_dev.argtypes = [vp, vp, sz, vp, vp]
     L.ecfft_enter_range_dev.argtypes = [vp, vp, sz, sz, sz, vp, vp]
+    L.ecfft_mg_prescale_dev.argtypes = [vp, sz, sz, vp, sz, vp, vp]
+    L.ecfft_mg_cross_dev.argtypes = [vp, sz, ci, ctypes.c_uint, ci, sz, vp, vp, sz, vp, vp]
+    L.ecfft_mg_local_dev.argtypes = [vp, sz, vp, sz, vp, vp]
+    L.ecfft_mg_combine_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp]
     L.ecfft_launch_count.restype = ctypes.c_ulonglong
     L.ecfft_launch_count.argtypes = []
     L.ecfft_profile_enable.restype = None

@@ -379,4 +379,48 @@ int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* 
   });
 }
 
+// ---- multi-GPU building blocks (include/ecfft_b200.h) ----------------------------------
+static uint32_t log2_exact(size_t v, const char* what) {
+  require(v && !(v & (v - 1)), ERR_NOT_POW2, what);
+  uint32_t l = 0;
+  while (((size_t)1 << l) < v) l++;
+  return l;
+}
+int ecfft_mg_prescale_dev(const ecfft_tree* t, size_t m, size_t pos0, const void* d_in, size_t count, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    const Level& lv = eng.level_for(m);
+    require(lv.gami[0] != nullptr, ERR_MISSING_TABLES, "normalised tables missing");
+    require(pos0 + count <= m / 2, ERR_INVALID_ARG, "slice exceeds the vector");
+    k::mul_bcast(dptr(d_out), dptr(d_in), lv.gami[0] + pos0, count, 1, eng.st);
+  });
+}
+int ecfft_mg_cross_dev(const ecfft_tree* t, size_t m, int phase, unsigned j, int role, size_t p_pos0, const void* d_own,
+                       const void* d_partner, size_t count, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    const Level& lv = eng.level_for(m);
+    require((phase == 0 || phase == 1) && (role == 0 || role == 1), ERR_INVALID_ARG, "bad phase/role");
+    require(((size_t)2 << j) <= m / 2 && p_pos0 + count <= m / 2, ERR_INVALID_ARG, "level or slice exceeds the vector");
+    k::mg_cross(lv, phase, j, role, p_pos0, dptr(d_own), dptr(d_partner), count, dptr(d_out), eng.st);
+  });
+}
+int ecfft_mg_local_dev(const ecfft_tree* t, size_t m, const void* d_in, size_t count, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    const Level& lv = eng.level_for(m);
+    require(count <= m / 2, ERR_INVALID_ARG, "chunk exceeds the vector");
+    k::extend_sub(lv, dptr(d_in), dptr(d_out), log2_exact(count, "chunk length is not a power of two"), eng.st);
+  });
+}
+int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d_u0, const void* d_v0, const void* d_u1,
+                         const void* d_v1, size_t count, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    const Level& lv = eng.level_for(m);
+    require(i0 + count <= m / 2, ERR_INVALID_ARG, "slice exceeds the block");
+    k::mg_combine(lv, i0, dptr(d_u0), dptr(d_v0), dptr(d_u1), dptr(d_v1), count, dptr(d_out), eng.st);
+  });
+}
+
 }  // extern "C"

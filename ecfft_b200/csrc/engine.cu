@@ -65,7 +65,7 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
   const Fp* cur = in;
   uint32_t idx = 0;
   // depths with block size <= 1024 run fused in shared memory (k_enter_small)
-  if (m_lo < 1024 && !getenv("ECFFT_B200_NO_SMALL_FUSION")) {
+  if (m_lo < 1024 && getenv("ECFFT_B200_SMALL_FUSION")) {  // opt-in: measured no faster (profiles/r01_f_*)
     const size_t m_small = m_hi < 1024 ? m_hi : 1024;
     Fp* dst = (m_small == m_hi && out != in) ? out : (ping[0] = tmp(n));
     if (k::enter_small(t.levels.data(), cur, dst, n, m_lo, m_small, st)) {

@@ -112,6 +112,9 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
             bool unscaled_out = false);
 // all ENTER depths m_lo < m <= m_hi <= 1024 in one shared-memory kernel; false if unavailable
 bool enter_small(const Level* levels, const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, cudaStream_t st);
+void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st);
+void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
+void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st);
 int butterfly_mode();  // 1 = normalised (default), 0 = 2x2 matrices (ECFFT_B200_BUTTERFLY=matrix)
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
 // scaling (lv.gam[1], lv.gx are used instead of xnn's odd entries).

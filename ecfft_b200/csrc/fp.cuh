@@ -309,33 +309,36 @@ FP_HD Fp fp_reduce(const MulAcc& A) {
   for (int k = 2; k < 16; k++) t[k] = addc_cc(A.e[k], A.o[k - 1]);
   t[16] = addc(A.e[16], 0u);
 
-  // r = lo + 977*hi + (hi << 32), hi = t[8..16]  (r < 2^291 -> 10 limbs)
+  // r = lo + 977*hi + (hi << 32), hi = t[8..16]  (r < 2^291 -> 10 limbs).
+  // Even-aligned chain: lo + 977*{t8,t10,t12,t14,t16}; odd-aligned chain (weight 2^32):
+  // 977*{t9,t11,t13,t15} + (hi << 32) taken as the 64-bit addends (t8,t9),(t10,t11),... — both chains
+  // write fresh aligned register pairs, so no limb has to change pair alignment (no moves).
+  uint32_t ev[10], od[9];
+  ev[0] = mad_lo_cc(t[8], FP_C977, t[0]);
+  ev[1] = madc_hi_cc(t[8], FP_C977, t[1]);
+  ev[2] = madc_lo_cc(t[10], FP_C977, t[2]);
+  ev[3] = madc_hi_cc(t[10], FP_C977, t[3]);
+  ev[4] = madc_lo_cc(t[12], FP_C977, t[4]);
+  ev[5] = madc_hi_cc(t[12], FP_C977, t[5]);
+  ev[6] = madc_lo_cc(t[14], FP_C977, t[6]);
+  ev[7] = madc_hi_cc(t[14], FP_C977, t[7]);
+  ev[8] = madc_lo_cc(t[16], FP_C977, 0u);
+  ev[9] = addc(0u, 0u);
+  od[0] = mad_lo_cc(t[9], FP_C977, t[8]);
+  od[1] = madc_hi_cc(t[9], FP_C977, t[9]);
+  od[2] = madc_lo_cc(t[11], FP_C977, t[10]);
+  od[3] = madc_hi_cc(t[11], FP_C977, t[11]);
+  od[4] = madc_lo_cc(t[13], FP_C977, t[12]);
+  od[5] = madc_hi_cc(t[13], FP_C977, t[13]);
+  od[6] = madc_lo_cc(t[15], FP_C977, t[14]);
+  od[7] = madc_hi_cc(t[15], FP_C977, t[15]);
+  od[8] = addc(t[16], 0u);
   uint32_t r[10];
-  r[0] = mad_lo_cc(t[8], FP_C977, t[0]);
-  r[1] = madc_hi_cc(t[8], FP_C977, t[1]);
-  r[2] = madc_lo_cc(t[10], FP_C977, t[2]);
-  r[3] = madc_hi_cc(t[10], FP_C977, t[3]);
-  r[4] = madc_lo_cc(t[12], FP_C977, t[4]);
-  r[5] = madc_hi_cc(t[12], FP_C977, t[5]);
-  r[6] = madc_lo_cc(t[14], FP_C977, t[6]);
-  r[7] = madc_hi_cc(t[14], FP_C977, t[7]);
-  r[8] = madc_lo_cc(t[16], FP_C977, 0u);
-  r[9] = addc(0u, 0u);
-
-  r[1] = mad_lo_cc(t[9], FP_C977, r[1]);
-  r[2] = madc_hi_cc(t[9], FP_C977, r[2]);
-  r[3] = madc_lo_cc(t[11], FP_C977, r[3]);
-  r[4] = madc_hi_cc(t[11], FP_C977, r[4]);
-  r[5] = madc_lo_cc(t[13], FP_C977, r[5]);
-  r[6] = madc_hi_cc(t[13], FP_C977, r[6]);
-  r[7] = madc_lo_cc(t[15], FP_C977, r[7]);
-  r[8] = madc_hi_cc(t[15], FP_C977, r[8]);
-  r[9] = addc(r[9], 0u);
-
-  r[1] = add_cc(r[1], t[8]);
+  r[0] = ev[0];
+  r[1] = add_cc(ev[1], od[0]);
 #pragma unroll
-  for (int k = 2; k < 9; k++) r[k] = addc_cc(r[k], t[k + 7]);
-  r[9] = addc(r[9], t[16]);
+  for (int k = 2; k < 9; k++) r[k] = addc_cc(ev[k], od[k - 1]);
+  r[9] = addc(ev[9], od[8]);
 
   // second fold: h2 = r[8] + r[9]*2^32 (< 2^35); V = h2*DELTA < 2^68
   uint32_t v0 = mul_lo(r[8], FP_C977);

@@ -380,6 +380,42 @@ void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, 
   });
 }
 
+// ------------------------------------------------------------------------------------------
+// multi-GPU building blocks: one butterfly level whose pairs straddle two ranks, and the
+// ENTER combine on a slice.  `own`/`partner` are the two ranks' chunks of the same vector, element e of
+// both belonging to the same pair; role 0: own holds the lower (p) element, 1: the upper (q) element.
+// ------------------------------------------------------------------------------------------
+void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st) {
+  const Fp* table = phase == 0 ? lv.tw_d[0] : lv.tw_r[1];
+  if (!table) throw Error(ERR_MISSING_TABLES, "mg_cross: normalised tables missing");
+  const Fp* layer = table + 2 * ((size_t)1 << j);
+  const size_t mask = ((size_t)1 << j) - 1, ibase = p_pos0 & mask;
+  map(count, st, [=] __device__(size_t e) {
+    const Fp* tw = layer + 2 * ((ibase + e) & mask);
+    Fp xo = fp_load(own + e), xr = fp_load(partner + e);
+    Fp xp = role == 0 ? xo : xr, xq = role == 0 ? xr : xo;
+    Fp res;
+    if (phase == 0) {  // decompose: y_q = c (x_q - x_p), y_p = x_p - s0 y_q
+      Fp yq = fp_mul_lazy(fp_load_ro(tw), fp_sub_lazy(xq, fp_canon(xp)));
+      res = role == 1 ? yq : fp_muladd_lazy(xp, fp_load_ro(tw + 1), yq);
+    } else {           // recombine: y_p = x_p + s0 x_q, y_q = x_p + s1 x_q
+      res = fp_muladd_lazy(xp, fp_load_ro(tw + role), xq);
+    }
+    fp_store(out + e, fp_canon(res));
+  });
+}
+// out[2t] = u0[t] + v0[t]*xnn[2(i0+t)], out[2t+1] = gam1[i0+t]*u1[t] + gx[i0+t]*v1[t]  (u1, v1 unscaled)
+void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st) {
+  if (!lv.gx || !lv.gam[1]) throw Error(ERR_MISSING_TABLES, "mg_combine: normalised tables missing");
+  const Fp* xnn = lv.xnn_s + 2 * i0;
+  const Fp* gam = lv.gam[1] + i0;
+  const Fp* gx = lv.gx + i0;
+  map(count, st, [=] __device__(size_t t) {
+    fp_store(out + 2 * t, fp_canon(fp_muladd_lazy(fp_load(u0 + t), fp_load(v0 + t), fp_load_ro(xnn + 2 * t))));
+    fp_store(out + 2 * t + 1, fp_canon(fp_dot2_lazy(fp_load_ro(gam + t), fp_load(u1 + t), fp_load_ro(gx + t), fp_load(v1 + t))));
+  });
+}
+
 // Normalised-butterfly tables of one chain level (DESIGN.md "twiddle form").  Entry idx = 2^j + i:
 // s0 = f[2B + 2i + mu], s1 = f[2B + 2i + mu + B] with B = 2^(j+1) — the same nodes the reference's
 // matrices are built from (src/fftree.rs:356-357) — through the strided view of the top tree's f.

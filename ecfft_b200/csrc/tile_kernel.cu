@@ -203,22 +203,10 @@ int butterfly_mode() {
   return mode;
 }
 
-void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st, bool unscaled_out) {
+// Schedules the tile passes for all levels j < log_h of vectors of length 2^log_h (p holds the tables,
+// mode and skips; pre/post are the per-position scales of the first load / last store or null).
+static void run_passes(TileParams p, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post, cudaStream_t st) {
   const uint32_t LT = log_tile();
-  if (nvec == 0) return;
-  if (log_h == 0) {  // extend_impl n == 1: identity, fftree.rs:74-76
-    if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, nvec * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
-    return;
-  }
-  TileParams p;
-  const Moiety source = target == S1 ? S0 : S1;
-  const bool norm = butterfly_mode() == 1 && lv.tw_r[target] && lv.tw_d[source] && lv.gam[target] && lv.gami[source];
-  if (unscaled_out && !norm) throw Error(ERR_INVALID_ARG, "extend: unscaled output needs the normalised tables");
-  p.norm = norm ? 1 : 0;
-  p.dmat = norm ? lv.tw_d[source] : lv.dmat;
-  p.rmat = norm ? lv.tw_r[target] : lv.rmat;
-  const Fp* pre = norm ? lv.gami[source] : nullptr;
-  const Fp* post = (norm && !unscaled_out) ? lv.gam[target] : nullptr;
   p.pre = nullptr;
   p.post = nullptr;
   p.nvec = nvec;
@@ -226,8 +214,6 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
   p.log_h = log_h;
   p.log_t = LT;
   p.packed = 0;
-  p.skip_d = target == S0 ? 1 : 0;  // fftree.rs:87-90
-  p.skip_r = target == S1 ? 1 : 0;  // fftree.rs:108-111
   if (log_h <= LT) {
     // whole vectors fit a tile: pack 2^(log_t-log_h) consecutive vectors per CTA
     p.in = in; p.out = out;
@@ -266,6 +252,43 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
     p.post = i == 0 ? post : nullptr;  // Gamma^target on the very last store
     launch_tile(p, st);
   }
+}
+
+void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st, bool unscaled_out) {
+  if (nvec == 0) return;
+  if (log_h == 0) {  // extend_impl n == 1: identity, fftree.rs:74-76
+    if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, nvec * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  TileParams p;
+  const Moiety source = target == S1 ? S0 : S1;
+  const bool norm = butterfly_mode() == 1 && lv.tw_r[target] && lv.tw_d[source] && lv.gam[target] && lv.gami[source];
+  if (unscaled_out && !norm) throw Error(ERR_INVALID_ARG, "extend: unscaled output needs the normalised tables");
+  p.norm = norm ? 1 : 0;
+  p.dmat = norm ? lv.tw_d[source] : lv.dmat;
+  p.rmat = norm ? lv.tw_r[target] : lv.rmat;
+  p.skip_d = target == S0 ? 1 : 0;  // fftree.rs:87-90
+  p.skip_r = target == S1 ? 1 : 0;  // fftree.rs:108-111
+  run_passes(p, in, out, log_h, nvec, norm ? lv.gami[source] : nullptr, (norm && !unscaled_out) ? lv.gam[target] : nullptr, st);
+}
+
+// Multi-GPU building block: the rank-local levels (half-strides < 2^log_len) of the normalised
+// EXTEND -> S1 of a longer vector whose contiguous chunk of 2^log_len elements this rank holds.
+// Twiddles depend only on the position modulo the half-stride, so the chunk behaves like a vector of
+// its own length with the long vector's tables; the diagonal scalings are applied by the caller.
+void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st) {
+  if (!(lv.tw_r[1] && lv.tw_d[0])) throw Error(ERR_MISSING_TABLES, "extend_sub: normalised tables missing");
+  if (log_len == 0) {
+    if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  TileParams p;
+  p.norm = 1;
+  p.dmat = lv.tw_d[0];
+  p.rmat = lv.tw_r[1];
+  p.skip_d = 0;
+  p.skip_r = 1;
+  run_passes(p, in, out, log_len, 1, nullptr, nullptr, st);
 }
 
 // ------------------------------------------------------------------------------------------

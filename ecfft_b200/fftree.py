@@ -228,6 +228,45 @@ class FFTree:
         return self._dev_call(self._L.ecfft_enter_range_dev, [data], data.shape[0], (m_lo, m_hi))
 
 
+    # ---- multi-GPU building blocks (device tensors only; include/ecfft_b200.h "fully sharded") ----
+    def _mg_out(self, like, rows):
+        import torch
+        return torch.empty((rows, 4), dtype=like.dtype, device=like.device)
+
+    def _stream(self, x):
+        import torch
+        return ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
+
+    def mg_prescale(self, m, pos0, x):
+        x = x.contiguous()
+        out = self._mg_out(x, x.shape[0])
+        _lib.check(self._L.ecfft_mg_prescale_dev(self._h, m, pos0, ctypes.c_void_p(x.data_ptr()), x.shape[0],
+                                                 ctypes.c_void_p(out.data_ptr()), self._stream(x)))
+        return out
+
+    def mg_cross(self, m, phase, j, role, p_pos0, own, partner):
+        own, partner = own.contiguous(), partner.contiguous()
+        out = self._mg_out(own, own.shape[0])
+        _lib.check(self._L.ecfft_mg_cross_dev(self._h, m, phase, j, role, p_pos0, ctypes.c_void_p(own.data_ptr()),
+                                              ctypes.c_void_p(partner.data_ptr()), own.shape[0],
+                                              ctypes.c_void_p(out.data_ptr()), self._stream(own)))
+        return out
+
+    def mg_local(self, m, x):
+        x = x.contiguous()
+        out = self._mg_out(x, x.shape[0])
+        _lib.check(self._L.ecfft_mg_local_dev(self._h, m, ctypes.c_void_p(x.data_ptr()), x.shape[0],
+                                              ctypes.c_void_p(out.data_ptr()), self._stream(x)))
+        return out
+
+    def mg_combine(self, m, i0, u0, v0, u1, v1):
+        u0, v0, u1, v1 = (t.contiguous() for t in (u0, v0, u1, v1))
+        out = self._mg_out(u0, 2 * u0.shape[0])
+        _lib.check(self._L.ecfft_mg_combine_dev(self._h, m, i0, *[ctypes.c_void_p(t.data_ptr()) for t in (u0, v0, u1, v1)],
+                                                u0.shape[0], ctypes.c_void_p(out.data_ptr()), self._stream(u0)))
+        return out
+
+
 class _SubtreeView:
     """`&FFTree` returned by subtree_with_size: same surface, restricted to n leaves."""
 

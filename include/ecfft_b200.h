@@ -107,6 +107,22 @@ int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* 
 int ecfft_enter_range_dev(const ecfft_tree* t, const void* d_in, size_t n, size_t m_lo, size_t m_hi,
                           void* d_out, void* stream);
 
+/* Fully sharded top depths (ecfft_b200/dist.py): for the ENTER depth with block size m
+ * (EXTEND of length-m/2 vectors towards S1) a rank holds a contiguous chunk of one vector.
+ *   prescale : out[e] = in[e] / Gamma^0[pos0 + e]                      (before the decompose levels)
+ *   cross    : one butterfly level (phase 0 decompose / 1 recombine, half-stride 2^j) whose pairs
+ *              straddle two ranks; role 0: this rank holds the lower elements; p_pos0 = position in
+ *              the vector of the first LOWER element; `partner` is the other rank's chunk
+ *   local    : all levels with half-stride < count on this rank's chunk
+ *   combine  : src/fftree.rs:155-159 for i in [i0, i0+count) of one block, u1/v1 still unscaled;
+ *              out has 2*count elements (positions 2*i0 .. of the block) */
+int ecfft_mg_prescale_dev(const ecfft_tree* t, size_t m, size_t pos0, const void* d_in, size_t count, void* d_out, void* stream);
+int ecfft_mg_cross_dev(const ecfft_tree* t, size_t m, int phase, unsigned j, int role, size_t p_pos0, const void* d_own,
+                       const void* d_partner, size_t count, void* d_out, void* stream);
+int ecfft_mg_local_dev(const ecfft_tree* t, size_t m, const void* d_in, size_t count, void* d_out, void* stream);
+int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d_u0, const void* d_v0, const void* d_u1,
+                         const void* d_v1, size_t count, void* d_out, void* stream);
+
 /* ---- instrumentation used by bench.py ------------------------------------------------- */
 /* kernels launched by this library since it was loaded */
 unsigned long long ecfft_launch_count(void);

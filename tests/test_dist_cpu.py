@@ -12,16 +12,111 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 
+P = 2**256 - 2**32 - 977
+
+
+def _ints(t):
+    return [r[0] | (r[1] << 64) | (r[2] << 128) | (r[3] << 192) for r in t.numpy().view(np.uint64).tolist()]
+
+
+def _tensor(vals):
+    a = np.array([[(v >> (64 * k)) & 0xFFFFFFFFFFFFFFFF for k in range(4)] for v in vals], dtype=np.uint64)
+    return torch.from_numpy(a.reshape(-1, 4).view(np.int64))
+
+
 class OracleBackedTree:
-    """stands in for ecfft_b200.FFTree.enter_range on CPU tensors"""
+    """Stands in for ecfft_b200.FFTree on CPU tensors: enter_range through the oracle's level-range
+    restatement, the multi-GPU building blocks as Python big-integer restatements of the normalised
+    butterflies with constants derived from the oracle's f and recombine tables."""
 
     def __init__(self, n):
         from oracle import oracle as O
+        self.O = O
         self.t = O.OracleTree.build(n, parts=1)
+        self._cache = {}
 
     def enter_range(self, data, m_lo, m_hi):
         arr = data.numpy().view(np.uint64)
         return torch.from_numpy(self.t.enter_range(arr, m_lo, m_hi).view(np.int64))
+
+    def _level(self, m):
+        if m in self._cache:
+            return self._cache[m]
+        O = self.O
+        st = self.t.subtree_with_size(m)
+        f = O.from_mont(st.table("f"))
+        rm = O.from_mont(st.table("recombine"))
+        xnn = O.from_mont(st.table("xnn_s"))
+        h = m // 2
+        tw = {}
+        for mu in (0, 1):
+            j = 0
+            while (1 << j) < h:
+                B = 2 << j
+                for i in range(1 << j):
+                    s0, s1 = f[2 * B + 2 * i + mu], f[2 * B + 2 * i + mu + B]
+                    tw[(mu, j, i)] = (s0, s1, pow(s1 - s0, -1, P))
+                j += 1
+        gam = {}
+        for mu in (0, 1):
+            g = []
+            for p in range(h):
+                acc, j = 1, 0
+                while (1 << j) < h:
+                    i, b = p & ((1 << j) - 1), (p >> j) & 1
+                    acc = acc * rm[4 * ((2 << j) + 2 * i + mu) + 2 * b] % P
+                    j += 1
+                g.append(acc)
+            gam[mu] = g
+        self._cache[m] = (tw, gam, xnn)
+        return self._cache[m]
+
+    def mg_prescale(self, m, pos0, x):
+        _, gam, _ = self._level(m)
+        return _tensor([v * pow(gam[0][pos0 + e], -1, P) % P for e, v in enumerate(_ints(x))])
+
+    def mg_cross(self, m, phase, j, role, p_pos0, own, partner):
+        tw, _, _ = self._level(m)
+        out = []
+        for e, (xo, xr) in enumerate(zip(_ints(own), _ints(partner))):
+            xp, xq = (xo, xr) if role == 0 else (xr, xo)
+            i = (p_pos0 + e) & ((1 << j) - 1)
+            if phase == 0:
+                s0, _, c = tw[(0, j, i)]
+                yq = c * (xq - xp) % P
+                out.append(yq if role == 1 else (xp - s0 * yq) % P)
+            else:
+                s0, s1, _ = tw[(1, j, i)]
+                out.append((xp + (s0 if role == 0 else s1) * xq) % P)
+        return _tensor(out)
+
+    def mg_local(self, m, x):
+        tw, _, _ = self._level(m)
+        v = _ints(x)
+        L = len(v).bit_length() - 1
+        for j in range(L - 1, -1, -1):
+            for p in range(len(v)):
+                if not (p >> j) & 1:
+                    s0, _, c = tw[(0, j, p & ((1 << j) - 1))]
+                    q = p + (1 << j)
+                    yq = c * (v[q] - v[p]) % P
+                    v[p], v[q] = (v[p] - s0 * yq) % P, yq
+        for j in range(L):
+            for p in range(len(v)):
+                if not (p >> j) & 1:
+                    s0, s1, _ = tw[(1, j, p & ((1 << j) - 1))]
+                    q = p + (1 << j)
+                    v[p], v[q] = (v[p] + s0 * v[q]) % P, (v[p] + s1 * v[q]) % P
+        return _tensor(v)
+
+    def mg_combine(self, m, i0, u0, v0, u1, v1):
+        _, gam, xnn = self._level(m)
+        out = []
+        for t, (a, b, c, d) in enumerate(zip(_ints(u0), _ints(v0), _ints(u1), _ints(v1))):
+            i = i0 + t
+            out.append((a + b * xnn[2 * i]) % P)
+            out.append(gam[1][i] * (c + d * xnn[2 * i + 1]) % P)
+        return _tensor(out)
 
 
 def _worker(rank, world, port, n, result_dir):
@@ -30,13 +125,17 @@ def _worker(rank, world, port, n, result_dir):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from oracle import oracle as O
-        from ecfft_b200.dist import enter_sharded
+        from ecfft_b200.dist import enter_sharded, enter_sharded_allgather
         tree = OracleBackedTree(n)
         x = O.random_elements(n, seed=11)
-        chunk = torch.from_numpy(x[rank * (n // world):(rank + 1) * (n // world)].view(np.int64).copy())
-        got = enter_sharded(tree, chunk, n).numpy().view(np.uint64)
+        c = n // world
+        chunk = torch.from_numpy(x[rank * c:(rank + 1) * c].view(np.int64).copy())
         want = tree.t.enter(x)
-        np.save(os.path.join(result_dir, f"ok_{rank}.npy"), np.array([(got == want).all()]))
+        ok = (enter_sharded_allgather(tree, chunk, n).numpy().view(np.uint64) == want).all()
+        ok = ok and (enter_sharded(tree, chunk, n).numpy().view(np.uint64) == want).all()
+        part = enter_sharded(tree, chunk, n, gather=False).numpy().view(np.uint64)
+        ok = ok and (part == want[rank * c:(rank + 1) * c]).all()
+        np.save(os.path.join(result_dir, f"ok_{rank}.npy"), np.array([ok]))
     finally:
         dist.destroy_process_group()
 
@@ -49,9 +148,9 @@ def _free_port():
     return port
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_enter_sharded_matches_single_enter(world, tmp_path):
-    n = 256
+    n = 128
     mp.spawn(_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
     for r in range(world):
         assert np.load(tmp_path / f"ok_{r}.npy")[0]
