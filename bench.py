@@ -24,6 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 METRIC = "secp256k1 Fp ENTER evals/sec at n=2^22"
+print_json = None
 UNIT = "evals/s"
 
 
@@ -138,10 +139,22 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print_json(line)
+
+
+def _protect_stdout():
+    """Libraries (NCCL's version banner, torchrun) write to fd 1; the contract is ONE JSON line on stdout.
+    Point fd 1 at stderr for the whole run and return a writer on the original stdout."""
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(saved, "w")
 
 
 def main():
+    real_stdout = _protect_stdout()
+    global print_json
+    print_json = lambda obj: (real_stdout.write(json.dumps(obj) + "\n"), real_stdout.flush())
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -330,7 +343,7 @@ def main():
         chk = tree.enter(host_np[last_e2e_in])
         line["e2e"]["matches_device_path"] = bool((chk == out_np).all())
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        print_json(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libecfft_b200.so")
+LIB_PATH = os.environ.get("ECFFT_B200_LIB") or os.path.join(_HERE, "lib", "libecfft_b200.so")  # override: A/B experiments only
 
 ECFFT_OK = 0
 ERR_NOT_POW2 = 1

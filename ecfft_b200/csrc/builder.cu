@@ -134,6 +134,9 @@ void build_norm_tables(Tree& t, uint32_t k) {
     k::build_gamma(lv.gam[mu], lv.rmat, hh, mu, st);
     ECFFT_CUDA(cudaMemcpyAsync(lv.gami[mu], lv.gam[mu], hh * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     k::batch_inverse(lv.gami[mu], hh, st);
+#ifndef ECFFT_D_DIFFFORM
+    k::fold_sumform_prescale(lv.gami[mu], t.f, stride, hh, mu, st);
+#endif
   }
   lv.gx = t.dalloc(hh);
   k::mul_strided(lv.gx, lv.gam[1], lv.xnn_s, 2, 1, hh, st);

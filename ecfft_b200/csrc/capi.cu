@@ -240,8 +240,39 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
   return guard([&] {
     LOCKED_IO
     eng.level_for(n);
-    Fp* d_in = io.in(coeffs, n);
+    require((coeffs != nullptr && evals != nullptr) || n == 0, ERR_INVALID_ARG, "null buffer");
     Fp* d_out = io.alloc(n);
+    // Large inputs: upload in PARTS chunks on a second stream while the compute stream already enters
+    // the chunks that have landed on the n/PARTS-leaf subtree (the recursion's own split,
+    // src/fftree.rs:150-151); only the first chunk's upload is exposed.
+    const size_t PARTS = 8;
+    if (n >= ((size_t)1 << 16)) {
+      const size_t c = n / PARTS;
+      Fp* d_in = io.alloc(n);
+      Fp* d_mid = io.alloc(n);
+      cudaStream_t cs = nullptr;
+      ECFFT_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      cudaEvent_t ev[PARTS];
+      try {
+        for (size_t g = 0; g < PARTS; g++) {
+          ECFFT_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
+          ECFFT_CUDA(cudaMemcpyAsync(d_in + g * c, coeffs + 4 * g * c, c * sizeof(Fp), cudaMemcpyHostToDevice, cs));
+          ECFFT_CUDA(cudaEventRecord(ev[g], cs));
+          ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[g], 0));
+          eng.enter_range(d_in + g * c, d_mid + g * c, c, 1, c);
+        }
+        eng.enter_range(d_mid, d_out, n, c, n);
+        io.out(evals, d_out, n);
+      } catch (...) {
+        cudaStreamSynchronize(cs);
+        cudaStreamDestroy(cs);
+        throw;
+      }
+      for (size_t g = 0; g < PARTS; g++) cudaEventDestroy(ev[g]);
+      cudaStreamDestroy(cs);
+      return;
+    }
+    Fp* d_in = io.in(coeffs, n);
     eng.enter(d_in, d_out, n);
     io.out(evals, d_out, n);
   });

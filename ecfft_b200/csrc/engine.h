@@ -152,6 +152,7 @@ void build_matrices(Fp* rmat_layer, Fp* dmat_layer, const Fp* flayer, size_t fst
 // normalised tables of one chain level (h = N/2 entries each); f_top strided by fstride is the level's f
 void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
 void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st);
+void fold_sumform_prescale(Fp* gami, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
 void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st);  // out[i] = a[i]*b[b_off + i*b_stride]
 }  // namespace k
 

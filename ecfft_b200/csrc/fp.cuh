@@ -214,6 +214,27 @@ FP_HD Fp fp_sub(const Fp& a, const Fp& b) {
 
 FP_HD Fp fp_neg(const Fp& a) { return fp_sub(fp_zero(), a); }
 
+// a + b mod p for lazy a, b in [0,2^256); lazy result.  A carry out of 2^256 folds back as +DELTA
+// (the wrapped sum is < 2^256 - 1, so adding DELTA can carry at most once more, which is folded too).
+FP_HD Fp fp_add_lazy(const Fp& a, const Fp& b) {
+  Fp s;
+  s.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) s.v[i] = addc_cc(a.v[i], b.v[i]);
+  uint32_t c = addc(0u, 0u);
+  uint32_t m = 0u - c;
+  s.v[0] = add_cc(s.v[0], m & FP_C977);
+  s.v[1] = addc_cc(s.v[1], c);
+#pragma unroll
+  for (int i = 2; i < 8; i++) s.v[i] = addc_cc(s.v[i], 0u);
+  uint32_t c2 = addc(0u, 0u);  // only if the wrapped sum was >= 2^256 - DELTA: then the result is tiny
+  uint32_t m2 = 0u - c2;
+  s.v[0] = add_cc(s.v[0], m2 & FP_C977);
+  s.v[1] = addc_cc(s.v[1], c2);
+  s.v[2] = addc(s.v[2], 0u);
+  return s;
+}
+
 // a - b mod p for lazy a in [0,2^256) and CANONICAL b; lazy result in [0,2^256)
 FP_HD Fp fp_sub_lazy(const Fp& a, const Fp& b) {
   Fp d;
@@ -309,6 +330,35 @@ FP_HD Fp fp_reduce(const MulAcc& A) {
   for (int k = 2; k < 16; k++) t[k] = addc_cc(A.e[k], A.o[k - 1]);
   t[16] = addc(A.e[16], 0u);
 
+#ifndef FP_REDUCE_ALIGNED   // default: three carry chains on one array — measured 5% faster in the tile kernel
+                          // than the move-free even/odd-aligned form below (profiles/r01_g_ab_variants.txt)
+  // r = lo + 977*hi + (hi << 32), hi = t[8..16]  (r < 2^291 -> 10 limbs): three chains on one array
+  uint32_t r[10];
+  r[0] = mad_lo_cc(t[8], FP_C977, t[0]);
+  r[1] = madc_hi_cc(t[8], FP_C977, t[1]);
+  r[2] = madc_lo_cc(t[10], FP_C977, t[2]);
+  r[3] = madc_hi_cc(t[10], FP_C977, t[3]);
+  r[4] = madc_lo_cc(t[12], FP_C977, t[4]);
+  r[5] = madc_hi_cc(t[12], FP_C977, t[5]);
+  r[6] = madc_lo_cc(t[14], FP_C977, t[6]);
+  r[7] = madc_hi_cc(t[14], FP_C977, t[7]);
+  r[8] = madc_lo_cc(t[16], FP_C977, 0u);
+  r[9] = addc(0u, 0u);
+  r[1] = mad_lo_cc(t[9], FP_C977, r[1]);
+  r[2] = madc_hi_cc(t[9], FP_C977, r[2]);
+  r[3] = madc_lo_cc(t[11], FP_C977, r[3]);
+  r[4] = madc_hi_cc(t[11], FP_C977, r[4]);
+  r[5] = madc_lo_cc(t[13], FP_C977, r[5]);
+  r[6] = madc_hi_cc(t[13], FP_C977, r[6]);
+  r[7] = madc_lo_cc(t[15], FP_C977, r[7]);
+  r[8] = madc_hi_cc(t[15], FP_C977, r[8]);
+  r[9] = addc(r[9], 0u);
+  r[1] = add_cc(r[1], t[8]);
+#pragma unroll
+  for (int k = 2; k < 9; k++) r[k] = addc_cc(r[k], t[k + 7]);
+  r[9] = addc(r[9], t[16]);
+
+#else
   // r = lo + 977*hi + (hi << 32), hi = t[8..16]  (r < 2^291 -> 10 limbs).
   // Even-aligned chain: lo + 977*{t8,t10,t12,t14,t16}; odd-aligned chain (weight 2^32):
   // 977*{t9,t11,t13,t15} + (hi << 32) taken as the 64-bit addends (t8,t9),(t10,t11),... — both chains
@@ -340,6 +390,7 @@ FP_HD Fp fp_reduce(const MulAcc& A) {
   for (int k = 2; k < 9; k++) r[k] = addc_cc(ev[k], od[k - 1]);
   r[9] = addc(ev[9], od[8]);
 
+#endif
   // second fold: h2 = r[8] + r[9]*2^32 (< 2^35); V = h2*DELTA < 2^68
   uint32_t v0 = mul_lo(r[8], FP_C977);
   uint32_t v1 = mul_hi(r[8], FP_C977) + r[9] * FP_C977;  // < 2^10 + 2^13

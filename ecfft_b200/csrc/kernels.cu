@@ -395,9 +395,13 @@ void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, c
     Fp xo = fp_load(own + e), xr = fp_load(partner + e);
     Fp xp = role == 0 ? xo : xr, xq = role == 0 ? xr : xo;
     Fp res;
-    if (phase == 0) {  // decompose: y_q = c (x_q - x_p), y_p = x_p - s0 y_q
+    if (phase == 0) {
+#ifndef ECFFT_D_DIFFFORM   // decompose, sum form: y_q = x^_p + x^_q, y_p = -(s1 x^_p + s0 x^_q)
+      res = role == 1 ? fp_add_lazy(xp, xq) : fp_dot2_lazy(fp_load_ro(tw), xp, fp_load_ro(tw + 1), xq);
+#else                    // decompose: y_q = c (x_q - x_p), y_p = x_p - s0 y_q
       Fp yq = fp_mul_lazy(fp_load_ro(tw), fp_sub_lazy(xq, fp_canon(xp)));
       res = role == 1 ? yq : fp_muladd_lazy(xp, fp_load_ro(tw + 1), yq);
+#endif
     } else {           // recombine: y_p = x_p + s0 x_q, y_q = x_p + s1 x_q
       res = fp_muladd_lazy(xp, fp_load_ro(tw + role), xq);
     }
@@ -432,8 +436,31 @@ void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t 
     Fp s1 = fp_load(f_top + (2 * B + 2 * i + mu + B) * fstride);
     fp_store(tw_r + 2 * idx, s0);
     fp_store(tw_r + 2 * idx + 1, s1);
+#ifndef ECFFT_D_DIFFFORM
+    fp_store(tw_d + 2 * idx, fp_neg(s1));
+    fp_store(tw_d + 2 * idx + 1, fp_neg(s0));
+#else
     fp_store(tw_d + 2 * idx, fp_inv(fp_sub(s1, s0)));
     fp_store(tw_d + 2 * idx + 1, fp_neg(s0));
+#endif
+  });
+}
+// Sum-form decompose: fold the per-level input scalings (-c for the lower, +c for the upper element of
+// each pair, c = 1/(s1-s0) of that level's pair) into the pre-scale table: gami[p] *= prod_j (+-c_j(p)).
+void fold_sumform_prescale(Fp* gami, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t p) {
+    Fp acc = fp_one();
+    bool neg = false;
+    for (uint32_t j = 0; ((size_t)1 << j) < h; j++) {
+      size_t i = p & (((size_t)1 << j) - 1), B = (size_t)2 << j;
+      Fp s0 = fp_load(f_top + (2 * B + 2 * i + mu) * fstride);
+      Fp s1 = fp_load(f_top + (2 * B + 2 * i + mu + B) * fstride);
+      acc = fp_mul(acc, fp_sub(s1, s0));
+      if (((p >> j) & 1) == 0) neg = !neg;
+    }
+    Fp c = fp_inv(acc);  // product of the c_j
+    if (neg) c = fp_neg(c);
+    fp_store(gami + p, fp_mul(fp_load(gami + p), c));
   });
 }
 // Gamma^mu_p = prod_j v(node_j(p))^(2^j - 1): exactly the first-column entries of the recombine

@@ -47,23 +47,44 @@ __device__ __forceinline__ void butterfly_matrix(Fp* s, uint32_t e_lo, uint32_t 
   s[e_hi] = y1;
 }
 // MODE 1 recombine: [[1, s0], [1, s1]] — the two outputs are x_p + s*x_q at the pair's two nodes
-__device__ __forceinline__ void butterfly_norm_r(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
-  Fp s0 = fp_load_ro(tw), s1 = fp_load_ro(tw + 1);
+__device__ __forceinline__ void butterfly_norm_r_v(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp& s0, const Fp& s1) {
   Fp xp = s[e_lo], xq = s[e_hi];
   s[e_lo] = fp_muladd_lazy(xp, s0, xq);
   s[e_hi] = fp_muladd_lazy(xp, s1, xq);
 }
-// MODE 1 decompose: inverse of [[1, s0], [1, s1]]: y_q = (x_q - x_p)/(s1 - s0), y_p = x_p - s0*y_q
+__device__ __forceinline__ void butterfly_norm_r(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
+  butterfly_norm_r_v(s, e_lo, e_hi, fp_load_ro(tw), fp_load_ro(tw + 1));
+}
+// MODE 1 decompose: inverse of [[1, s0], [1, s1]].
+#ifndef ECFFT_D_DIFFFORM
+// Sum form: input (column) scalings commute backwards through the decompose phase, so with
+// x^_p = -c x_p, x^_q = c x_q (c = 1/(s1-s0), folded into the 1/Gamma pre-scale table) the pair is
+// y_q = x^_p + x^_q (no multiplication), y_p = -(s1 x^_p + s0 x^_q) (two products, ONE reduction).
+// tw = {-s1, -s0}
+__device__ __forceinline__ void butterfly_norm_d_v(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp& ns1, const Fp& ns0) {
+  Fp xp = s[e_lo], xq = s[e_hi];
+  s[e_hi] = fp_add_lazy(xp, xq);
+  s[e_lo] = fp_dot2_lazy(ns1, xp, ns0, xq);
+}
 __device__ __forceinline__ void butterfly_norm_d(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
-  Fp c = fp_load_ro(tw), ns0 = fp_load_ro(tw + 1);
+  butterfly_norm_d_v(s, e_lo, e_hi, fp_load_ro(tw), fp_load_ro(tw + 1));
+}
+#else
+// y_q = (x_q - x_p)/(s1 - s0), y_p = x_p - s0*y_q;  tw = {1/(s1-s0), -s0}
+__device__ __forceinline__ void butterfly_norm_d_v(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp& c, const Fp& ns0) {
   Fp xp = fp_canon(s[e_lo]), xq = s[e_hi];
   Fp yq = fp_mul_lazy(c, fp_sub_lazy(xq, xp));
   s[e_hi] = yq;
   s[e_lo] = fp_muladd_lazy(xp, ns0, yq);
 }
+__device__ __forceinline__ void butterfly_norm_d(Fp* s, uint32_t e_lo, uint32_t e_hi, const Fp* tw) {
+  butterfly_norm_d_v(s, e_lo, e_hi, fp_load_ro(tw), fp_load_ro(tw + 1));
+}
+#endif
 
-template <int MODE, int NT, int MINB, int UNROLL>
+template <int MODE, int NT, int MINB, int UNROLL, int PF = 0>
 __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
+  static_assert(MODE == 0 || MODE == 1, "butterfly mode");
   extern __shared__ uint4 smem_raw[];
   Fp* s = reinterpret_cast<Fp*>(smem_raw);
   const uint32_t T = 1u << p.log_t;
@@ -97,6 +118,25 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
       const uint32_t sh = (uint32_t)j - p.j_lo + p.log_c;  // bit of the tile index that this level pairs
       const unsigned long long jmask = (1ull << j) - 1;
       const Fp* layer = MODE == 0 ? p.dmat + 4 * ((2ull << j) + p.skip_d) : p.dmat + 2 * (1ull << j);
+      if (MODE == 1 && PF) {  // software pipelining: the next pair's twiddles load while this pair computes
+        uint32_t b = threadIdx.x;
+        uint32_t e_nx = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
+        const Fp* tw = layer + 2 * ((pos0 + ((unsigned long long)(e_nx >> p.log_c) << p.j_lo) + (e_nx & (C - 1))) & jmask);
+        Fp t0 = fp_load_ro(tw), t1 = fp_load_ro(tw + 1);
+#pragma unroll 1
+        for (; b < T / 2; b += NT) {
+          const uint32_t e_lo = e_nx;
+          const Fp c0 = t0, c1 = t1;
+          if (b + NT < T / 2) {
+            const uint32_t bn = b + NT;
+            e_nx = ((bn >> sh) << (sh + 1)) | (bn & ((1u << sh) - 1));
+            tw = layer + 2 * ((pos0 + ((unsigned long long)(e_nx >> p.log_c) << p.j_lo) + (e_nx & (C - 1))) & jmask);
+            t0 = fp_load_ro(tw);
+            t1 = fp_load_ro(tw + 1);
+          }
+          butterfly_norm_d_v(s, e_lo, e_lo + (1u << sh), c0, c1);
+        }
+      } else {
 #pragma unroll UNROLL
       for (uint32_t b = threadIdx.x; b < T / 2; b += NT) {
         uint32_t e_lo = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
@@ -107,6 +147,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
         else
           butterfly_norm_d(s, e_lo, e_lo + (1u << sh), layer + 2 * i);
       }
+      }
       __syncthreads();
     }
   }
@@ -115,6 +156,25 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
       const uint32_t sh = j - p.j_lo + p.log_c;
       const unsigned long long jmask = (1ull << j) - 1;
       const Fp* layer = MODE == 0 ? p.rmat + 4 * ((2ull << j) + p.skip_r) : p.rmat + 2 * (1ull << j);
+      if (MODE == 1 && PF) {  // software pipelining: the next pair's twiddles load while this pair computes
+        uint32_t b = threadIdx.x;
+        uint32_t e_nx = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
+        const Fp* tw = layer + 2 * ((pos0 + ((unsigned long long)(e_nx >> p.log_c) << p.j_lo) + (e_nx & (C - 1))) & jmask);
+        Fp t0 = fp_load_ro(tw), t1 = fp_load_ro(tw + 1);
+#pragma unroll 1
+        for (; b < T / 2; b += NT) {
+          const uint32_t e_lo = e_nx;
+          const Fp c0 = t0, c1 = t1;
+          if (b + NT < T / 2) {
+            const uint32_t bn = b + NT;
+            e_nx = ((bn >> sh) << (sh + 1)) | (bn & ((1u << sh) - 1));
+            tw = layer + 2 * ((pos0 + ((unsigned long long)(e_nx >> p.log_c) << p.j_lo) + (e_nx & (C - 1))) & jmask);
+            t0 = fp_load_ro(tw);
+            t1 = fp_load_ro(tw + 1);
+          }
+          butterfly_norm_r_v(s, e_lo, e_lo + (1u << sh), c0, c1);
+        }
+      } else {
 #pragma unroll UNROLL
       for (uint32_t b = threadIdx.x; b < T / 2; b += NT) {
         uint32_t e_lo = ((b >> sh) << (sh + 1)) | (b & ((1u << sh) - 1));
@@ -124,6 +184,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
           butterfly_matrix(s, e_lo, e_lo + (1u << sh), layer + 8 * i);
         else
           butterfly_norm_r(s, e_lo, e_lo + (1u << sh), layer + 2 * i);
+      }
       }
       __syncthreads();
     }
@@ -140,30 +201,37 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
 }
 
 // Launch-shape variants (ECFFT_B200_TILE_VARIANT, measured in profiles/):
-//   0: 256 threads, 2048-element tile, butterfly loop unrolled x4 (100 registers, 2 CTAs/SM)
-//   1: 256 threads, 2048-element tile, no unrolling (78 registers, 3 CTAs/SM) — default, fastest
-//   2: 256 threads, 3 CTAs/SM (<= 85 registers), 2048-element tile
+//   0: 256 threads, 2048-element tile, butterfly loop unrolled x4 (2 CTAs/SM)
+//   1: 256 threads, 2048-element tile, no unrolling (3 CTAs/SM fit) — default
+//   2: as 1 with __launch_bounds__(256, 3)
 //   3: 512 threads, 1 CTA/SM, 4096-element tile (12 + 12 levels in the inner pass)
 //   4: 512 threads, 1 CTA/SM, 2048-element tile
+//   5: as 1 with the butterfly loop unrolled x2
+//   6: 128 threads, 1024-element tile, __launch_bounds__(128, 4)
+//   7: 128 threads, 1024-element tile, __launch_bounds__(128, 6)
+//   8: as 1 with software-prefetched twiddles
 static int tile_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ECFFT_B200_TILE_VARIANT");
     v = e ? atoi(e) : 1;
-    if (v < 0 || v > 4) v = 1;
+    if (v < 0 || v > 8) v = 1;
   }
   return v;
 }
-static uint32_t log_tile() { return tile_variant() == 3 ? 12 : 11; }
+static uint32_t log_tile() {
+  int v = tile_variant();
+  return v == 3 ? 12 : (v == 6 || v == 7) ? 10 : 11;
+}
 
-template <int MODE, int NT, int MINB, int UNROLL>
+template <int MODE, int NT, int MINB, int UNROLL, int PF = 0>
 static void launch_variant(const TileParams& p, size_t tiles, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<MODE, NT, MINB, UNROLL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 12) * sizeof(Fp))));
+    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<MODE, NT, MINB, UNROLL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 12) * sizeof(Fp))));
     configured = true;
   }
-  k_extend_tile<MODE, NT, MINB, UNROLL><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
+  k_extend_tile<MODE, NT, MINB, UNROLL, PF><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
 }
 
 static void launch_tile(const TileParams& p, cudaStream_t st) {
@@ -186,6 +254,10 @@ static void launch_tile(const TileParams& p, cudaStream_t st) {
       case 2: launch_variant<1, 256, 3, 1>(p, tiles, st); break;
       case 3: launch_variant<1, 512, 1, 1>(p, tiles, st); break;
       case 4: launch_variant<1, 512, 1, 1>(p, tiles, st); break;
+      case 5: launch_variant<1, 256, 2, 2>(p, tiles, st); break;
+      case 6: launch_variant<1, 128, 4, 1>(p, tiles, st); break;
+      case 7: launch_variant<1, 128, 6, 1>(p, tiles, st); break;
+      case 8: launch_variant<1, 256, 2, 1, 1>(p, tiles, st); break;
       default: launch_variant<1, 256, 2, 1>(p, tiles, st); break;
     }
   }

@@ -14,9 +14,40 @@ Two schedules for the top log2(G) depths:
   level), rank-local levels run the usual tile kernel on the chunk, and the combine exchanges
   half-chunks with the sibling vector's ranks.  Per-rank work is ~1/G of the total; one final
   all-gather returns the full evaluation vector on every rank (the reference's `Vec<F>` result).
+
+The schedule talks to its peers through a small comm object so that tests can run it with virtual
+ranks (threads) on one device; `TorchComm` is the real one.
 """
 import torch
 import torch.distributed as dist
+
+
+class TorchComm:
+    """pairwise exchanges and the final all-gather over a torch.distributed process group"""
+
+    def __init__(self, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def sendrecv(self, sends, recvs):
+        """sends: [(tensor, dst)], recvs: [(rows, like_tensor, src)] -> received tensors in order"""
+        ops, out = [], []
+        for tensor, dst in sends:
+            ops.append(dist.P2POp(dist.isend, tensor.contiguous(), dst, self.group))
+        for rows, like, src in recvs:
+            buf = torch.empty((rows, 4), dtype=like.dtype, device=like.device)
+            out.append(buf)
+            ops.append(dist.P2POp(dist.irecv, buf, src, self.group))
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return out
+
+    def all_gather(self, tensor):
+        out = torch.empty((tensor.shape[0] * self.world, 4), dtype=tensor.dtype, device=tensor.device)
+        dist.all_gather_into_tensor(out, tensor.contiguous(), group=self.group)
+        return out
 
 
 def _check(n, world, chunk):
@@ -26,33 +57,22 @@ def _check(n, world, chunk):
         raise ValueError("chunk must hold n / world_size coefficients")
 
 
-def enter_sharded_allgather(tree, chunk, n, group=None):
+def enter_sharded_allgather(tree, chunk, n, group=None, comm=None):
     """chunk: this rank's n/G coefficients ((n/G, 4) limb tensor, rank order = coefficient order).
     Returns the full evaluation vector (n, 4) on every rank."""
-    world = dist.get_world_size(group)
-    _check(n, world, chunk)
-    local = tree.enter_range(chunk, 1, n // world)
-    if world == 1:
+    comm = comm or TorchComm(group)
+    _check(n, comm.world, chunk)
+    local = tree.enter_range(chunk, 1, n // comm.world)
+    if comm.world == 1:
         return local
-    gathered = torch.empty((n, 4), dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(gathered, local, group=group)
-    return tree.enter_range(gathered, n // world, n)
+    return tree.enter_range(comm.all_gather(local), n // comm.world, n)
 
 
-def _exchange(send, peer, group):
-    """pairwise exchange of equal-sized tensors with `peer`"""
-    recv = torch.empty_like(send)
-    ops = [dist.P2POp(dist.isend, send, peer, group), dist.P2POp(dist.irecv, recv, peer, group)]
-    for w in dist.batch_isend_irecv(ops):
-        w.wait()
-    return recv
-
-
-def enter_sharded(tree, chunk, n, group=None, gather=True):
+def enter_sharded(tree, chunk, n, group=None, gather=True, comm=None):
     """Fully sharded ENTER.  Returns the full (n, 4) evaluation vector on every rank (gather=True) or
     this rank's chunk of it, positions [rank*n/G, (rank+1)*n/G)."""
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
+    comm = comm or TorchComm(group)
+    world, rank = comm.world, comm.rank
     _check(n, world, chunk)
     c = n // world
     log_c = c.bit_length() - 1
@@ -71,44 +91,39 @@ def enter_sharded(tree, chunk, n, group=None, gather=True):
         for j in range(log_h - 1, log_c - 1, -1):           # decompose levels whose pairs straddle ranks
             bit = (k >> (j - log_c)) & 1
             peer = rank ^ (1 << (j - log_c))
-            P = _exchange(W, peer, group)
+            (P,) = comm.sendrecv([(W, peer)], [(c, W, peer)])
             W = tree.mg_cross(m, 0, j, bit, pos0 - (bit << j), W, P)
         W = tree.mg_local(m, W)                             # all levels with half-stride < c
         for j in range(log_c, log_h):                       # recombine levels that straddle ranks
             bit = (k >> (j - log_c)) & 1
             peer = rank ^ (1 << (j - log_c))
-            P = _exchange(W, peer, group)
+            (P,) = comm.sendrecv([(W, peer)], [(c, W, peer)])
             W = tree.mg_cross(m, 1, j, bit, pos0 - (bit << j), W, P)
         # ---- combine (src/fftree.rs:155-159): output rank k' of the block needs i in [k'c/2, (k'+1)c/2)
         # of u0,u1 (from u-rank k'//2) and v0,v1 (from v-rank k'//2)
         is_u = vidx % 2 == 0
         half = c // 2
-        mine = torch.cat([A, W])                            # [x0 | x1] of my vector chunk
-        dests = [block0 + 2 * k, block0 + 2 * k + 1]        # output ranks fed by my two halves
         kp = rank - block0                                  # my output-rank index in the block
         usrc, vsrc = block0 + kp // 2, block0 + r + kp // 2
-        want = kp % 2                                       # which half of the sources' chunks I need
-        ops, bufs = [], {}
-        for hsel, dst in enumerate(dests):
-            part = torch.cat([mine[hsel * half:(hsel + 1) * half], mine[c + hsel * half:c + (hsel + 1) * half]])
+        parts = {}
+        sends, recvs, names = [], [], []
+        for hsel in (0, 1):                                 # my two halves feed output ranks 2k and 2k+1
+            dst = block0 + 2 * k + hsel
+            part = torch.cat([A[hsel * half:(hsel + 1) * half], W[hsel * half:(hsel + 1) * half]])
             if dst == rank:
-                bufs["u" if is_u else "v"] = part
+                parts["u" if is_u else "v"] = part
             else:
-                ops.append(dist.P2POp(dist.isend, part, dst, group))
+                sends.append((part, dst))
         for name, src in (("u", usrc), ("v", vsrc)):
             if src != rank:
-                bufs[name] = torch.empty((2 * half, 4), dtype=A.dtype, device=A.device)
-                ops.append(dist.P2POp(dist.irecv, bufs[name], src, group))
-        if ops:
-            for w in dist.batch_isend_irecv(ops):
-                w.wait()
-        u, v = bufs["u"], bufs["v"]
+                recvs.append((2 * half, A, src))
+                names.append(name)
+        for name, buf in zip(names, comm.sendrecv(sends, recvs)):
+            parts[name] = buf
+        u, v = parts["u"], parts["v"]
         A = tree.mg_combine(m, kp * half, u[:half], v[:half], u[half:], v[half:])
-        del want
         r *= 2
         m *= 2
     if not gather or world == 1:
         return A
-    out = torch.empty((n, 4), dtype=A.dtype, device=A.device)
-    dist.all_gather_into_tensor(out, A, group=group)
-    return out
+    return comm.all_gather(A)

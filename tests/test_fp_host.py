@@ -72,6 +72,9 @@ def test_add_sub_mont(shim):
         assert dec(out) == (a + b) % P
         shim.fph_sub(enc(a), enc(b), out)
         assert dec(out) == (a - b) % P
+        l1, l2 = rnd(r), rnd(r)                      # lazy + lazy (any 256-bit patterns)
+        shim.fph_add_lazy(enc(l1), enc(l2), out)
+        assert dec(out) % P == (l1 + l2) % P
         lazy = rnd(r)                                # any 256-bit pattern minus a canonical value
         shim.fph_sub_lazy(enc(lazy), enc(b), out)
         assert dec(out) % P == (lazy - b) % P

@@ -312,49 +312,64 @@ def test_full_size_extend_redc_mod(tree22, oracle_mod):
     assert tree22.degree(h) < n // 2
 
 
-def test_multi_gpu_building_blocks_match_cpu_emulation(oracle_mod):
-    """ecfft_mg_{prescale,cross,local,combine}_dev against the Python big-integer restatement that the
-    gloo tests (tests/test_dist_cpu.py) validate the sharded schedule with"""
+class _ThreadComm:
+    """virtual ranks as threads on one device: FIFO mailboxes per (src, dst) pair"""
+
+    def __init__(self, rank, world, boxes, slots, barrier):
+        self.rank, self.world, self.boxes, self.slots, self.barrier = rank, world, boxes, slots, barrier
+
+    def sendrecv(self, sends, recvs):
+        for tensor, dst in sends:
+            self.boxes[(self.rank, dst)].put(tensor.clone())
+        return [self.boxes[(src, self.rank)].get(timeout=120) for _, _, src in recvs]
+
+    def all_gather(self, tensor):
+        import torch
+        self.slots[self.rank] = tensor
+        self.barrier.wait()
+        out = torch.cat([self.slots[r] for r in range(self.world)])
+        self.barrier.wait()
+        return out
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_schedule_with_virtual_ranks(trees, oracle_mod, world):
+    """The fully sharded multi-GPU ENTER (ecfft_b200/dist.py) with `world` virtual ranks on ONE GPU: every
+    building block of the C ABI (ecfft_mg_*_dev, ecfft_enter_range_dev) in composition == the oracle"""
+    import queue
+    import threading
     import torch
-    import ecfft_b200
-    from tests.test_dist_cpu import OracleBackedTree
-    n = 256
-    gpu = ecfft_b200.build_fftree(n, parts=ecfft_b200.PARTS_ENTER_ONLY)
-    emu = OracleBackedTree(n)
-    cpu = lambda a: torch.from_numpy(a.view(np.int64).copy())
-    dev = lambda a: cpu(a).cuda()
-    back = lambda t: t.cpu().numpy().view(np.uint64)
-    for m, c in ((256, 32), (128, 64), (64, 8)):
-        h = m // 2
-        x = oracle_mod.random_elements(c, seed=m)
-        y = oracle_mod.random_elements(c, seed=m + 1)
-        for pos0 in (0, h - c):
-            eq(back(gpu.mg_prescale(m, pos0, dev(x))), back(emu.mg_prescale(m, pos0, cpu(x))))
-        log_c, log_h = c.bit_length() - 1, h.bit_length() - 1
-        for phase in (0, 1):
-            for j in range(log_c, log_h):
-                for role in (0, 1):
-                    p_pos0 = 0 if role == 0 else 0
-                    got = gpu.mg_cross(m, phase, j, role, p_pos0, dev(x), dev(y))
-                    eq(back(got), back(emu.mg_cross(m, phase, j, role, p_pos0, cpu(x), cpu(y))))
-                    p_pos0 = (1 << j) - c if (1 << j) >= c else 0
-                    got = gpu.mg_cross(m, phase, j, role, p_pos0, dev(x), dev(y))
-                    eq(back(got), back(emu.mg_cross(m, phase, j, role, p_pos0, cpu(x), cpu(y))))
-        eq(back(gpu.mg_local(m, dev(x))), back(emu.mg_local(m, cpu(x))))
-        half = c // 2
-        a, b = x[:half], x[half:]
-        d, e = y[:half], y[half:]
-        for i0 in (0, h - half):
-            eq(back(gpu.mg_combine(m, i0, dev(a), dev(b), dev(d), dev(e))),
-               back(emu.mg_combine(m, i0, cpu(a), cpu(b), cpu(d), cpu(e))))
-    # a chunk longer than one shared-memory tile through the local path == plain EXTEND of that length
-    big = ecfft_b200.build_fftree(1 << 14, parts=ecfft_b200.PARTS_ENTER_ONLY)
-    xs = oracle_mod.random_elements(1 << 13, seed=9)
-    whole = back(big.mg_local(1 << 14, dev(xs)))
-    pre = back(big.mg_prescale(1 << 14, 0, dev(xs)))
-    ext = back(big.extend(dev(xs), 1))
-    # EXTEND = Gamma^1 * local(prescaled): check through the scaling-free identity local(pre) vs extend/gam
-    again = back(big.mg_local(1 << 14, dev(pre)))
-    gam_inv_applied = back(big.mg_combine(1 << 14, 0, dev(np.zeros_like(xs)), dev(np.zeros_like(xs)), dev(again), dev(np.zeros_like(xs))))
-    eq(gam_inv_applied[1::2], ext)      # out[2t+1] = gam1[t] * u1[t] + gx[t] * 0
-    assert whole.shape == ext.shape
+    from ecfft_b200.dist import enter_sharded, enter_sharded_allgather
+    gpu, cpu = trees
+    n = 1 << 14
+    x = oracle_mod.random_elements(n, seed=world)
+    want = cpu.enter(x)
+    xd = torch.from_numpy(x.view(np.int64)).cuda()
+    c = n // world
+    boxes = {(a, b): queue.Queue() for a in range(world) for b in range(world)}
+    slots, barrier = [None] * world, threading.Barrier(world)
+    results, errors = [None] * world, []
+
+    def run(rank):
+        try:
+            comm = _ThreadComm(rank, world, boxes, slots, barrier)
+            full = enter_sharded(gpu, xd[rank * c:(rank + 1) * c], n, comm=comm)
+            part = enter_sharded(gpu, xd[rank * c:(rank + 1) * c], n, comm=comm, gather=False)
+            ag = enter_sharded_allgather(gpu, xd[rank * c:(rank + 1) * c], n, comm=comm)
+            torch.cuda.synchronize()
+            results[rank] = (full.cpu().numpy().view(np.uint64), part.cpu().numpy().view(np.uint64), ag.cpu().numpy().view(np.uint64))
+        except Exception as e:  # surface failures instead of deadlocking the other ranks
+            errors.append(repr(e))
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    for rank in range(world):
+        full, part, ag = results[rank]
+        eq(full, want)
+        eq(ag, want)
+        eq(part, want[rank * c:(rank + 1) * c])
