@@ -38,6 +38,19 @@ def alg_bytes_per_elem(log_n):
     return 64 * log_n * (log_n - 1) + 256 + 128 * log_n
 
 
+def ncu_traffic(log_n):
+    """DRAM bytes the dominant kernel moved per step in the committed ncu capture (profiles/), n = 2^22 only"""
+    if log_n != 22:
+        return None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        k = t["k_extend_tile"]
+        return k["dram_total_gb_per_step"], f"GB per step over {k['launches_per_step']} launches (profiles/r01_traffic.json; algorithmic bytes are per step too)"
+    except Exception:
+        return None, None
+
+
 def measured_peak():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -317,7 +330,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {
             "kernel": "k_extend_tile", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-            "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+            "frac": achieved / peak, "traffic": ncu_traffic(log_n)[0], "traffic_unit": ncu_traffic(log_n)[1],
+            "peak_source": peak_src,
             "kernel_ms_per_step": dom["ms_per_step"], "alg_gb_per_step": dom["alg_gb_per_step"],
             "launches_per_step": dom["launches_per_step"],
             "whole_step": {"alg_gb": alg_bytes_per_elem(log_n) * n / 1e9,

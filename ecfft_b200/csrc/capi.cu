@@ -244,8 +244,9 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
     Fp* d_out = io.alloc(n);
     // Large inputs: upload in PARTS chunks on a second stream while the compute stream already enters
     // the chunks that have landed on the n/PARTS-leaf subtree (the recursion's own split,
-    // src/fftree.rs:150-151); only the first chunk's upload is exposed.
-    const size_t PARTS = 8;
+    // src/fftree.rs:150-151); only the first chunk's upload is exposed.  Two halves: smaller chunks
+    // under-fill the GPU (measured: 8 parts cost +6 ms at n = 2^22).
+    const size_t PARTS = 2;
     if (n >= ((size_t)1 << 16)) {
       const size_t c = n / PARTS;
       Fp* d_in = io.alloc(n);

@@ -202,20 +202,20 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
 
 // Launch-shape variants (ECFFT_B200_TILE_VARIANT, measured in profiles/):
 //   0: 256 threads, 2048-element tile, butterfly loop unrolled x4 (2 CTAs/SM)
-//   1: 256 threads, 2048-element tile, no unrolling (3 CTAs/SM fit) — default
+//   1: 256 threads, 2048-element tile, no unrolling (3 CTAs/SM fit)
 //   2: as 1 with __launch_bounds__(256, 3)
 //   3: 512 threads, 1 CTA/SM, 4096-element tile (12 + 12 levels in the inner pass)
 //   4: 512 threads, 1 CTA/SM, 2048-element tile
 //   5: as 1 with the butterfly loop unrolled x2
 //   6: 128 threads, 1024-element tile, __launch_bounds__(128, 4)
-//   7: 128 threads, 1024-element tile, __launch_bounds__(128, 6)
+//   7: 128 threads, 1024-element tile, __launch_bounds__(128, 6): 72 registers, 7 CTAs/SM — default, fastest
 //   8: as 1 with software-prefetched twiddles
 static int tile_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ECFFT_B200_TILE_VARIANT");
-    v = e ? atoi(e) : 1;
-    if (v < 0 || v > 8) v = 1;
+    v = e ? atoi(e) : 7;
+    if (v < 0 || v > 8) v = 7;
   }
   return v;
 }
@@ -251,14 +251,14 @@ static void launch_tile(const TileParams& p, cudaStream_t st) {
   } else {
     switch (tile_variant()) {
       case 0: launch_variant<1, 256, 2, 4>(p, tiles, st); break;
+      case 1: launch_variant<1, 256, 2, 1>(p, tiles, st); break;
       case 2: launch_variant<1, 256, 3, 1>(p, tiles, st); break;
       case 3: launch_variant<1, 512, 1, 1>(p, tiles, st); break;
       case 4: launch_variant<1, 512, 1, 1>(p, tiles, st); break;
       case 5: launch_variant<1, 256, 2, 2>(p, tiles, st); break;
       case 6: launch_variant<1, 128, 4, 1>(p, tiles, st); break;
-      case 7: launch_variant<1, 128, 6, 1>(p, tiles, st); break;
       case 8: launch_variant<1, 256, 2, 1, 1>(p, tiles, st); break;
-      default: launch_variant<1, 256, 2, 1>(p, tiles, st); break;
+      default: launch_variant<1, 128, 6, 1>(p, tiles, st); break;
     }
   }
   if (timed) prof::record_end(st);

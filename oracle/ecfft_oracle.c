@@ -681,14 +681,110 @@ int orc_enter(const orc_tree* t, const fe* coeffs, size_t n, fe* out) {
   enter_impl(s, coeffs, n, out, 0);
   return 0;
 }
+/* All-cores variant of enter_impl / extend_impl for the CPU baseline: identical arithmetic and
+ * recursion; a thread budget is split between the two independent recursive calls and the butterfly /
+ * combine loops are cut into ranges across the budget (plain pthreads; the image has no OpenMP
+ * runtime).  The reference library itself is single-threaded. */
+typedef struct { void (*fn)(size_t, size_t, void*); size_t lo, hi; void* ctx; } pf_job;
+static void* pf_thread(void* p) {
+  pf_job* j = (pf_job*)p;
+  j->fn(j->lo, j->hi, j->ctx);
+  return NULL;
+}
+static void parallel_for(size_t n, int threads, void (*fn)(size_t, size_t, void*), void* ctx) {
+  if (threads > 64) threads = 64;
+  if (threads <= 1 || n < 2048) {
+    fn(0, n, ctx);
+    return;
+  }
+  pthread_t th[64];
+  pf_job jobs[64];
+  for (int k = 0; k < threads; k++) {
+    jobs[k].fn = fn;
+    jobs[k].lo = n * (size_t)k / threads;
+    jobs[k].hi = n * (size_t)(k + 1) / threads;
+    jobs[k].ctx = ctx;
+    if (k < threads - 1) pthread_create(&th[k], NULL, pf_thread, &jobs[k]);
+  }
+  fn(jobs[threads - 1].lo, jobs[threads - 1].hi, ctx);
+  for (int k = 0; k < threads - 1; k++) pthread_join(th[k], NULL);
+}
+typedef struct { const fe* mats; int skip; const fe *a, *b; fe *y0, *y1; } bf_ctx;
+static void bf_range(size_t lo, size_t hi, void* p) {
+  bf_ctx* c = (bf_ctx*)p;
+  for (size_t i = lo; i < hi; i++) matvec(c->mats + 4 * (2 * i + c->skip), &c->a[i], &c->b[i], &c->y0[i], &c->y1[i]);
+}
+typedef struct { const orc_tree* t; const fe* in; size_t n; int moiety; fe* out; int threads; } mt_job;
+static void extend_mt(const orc_tree* t, const fe* evals, size_t n, int moiety, fe* out, int threads);
+static void* extend_mt_thread(void* p) {
+  mt_job* j = (mt_job*)p;
+  extend_mt(j->t, j->in, j->n, j->moiety, j->out, j->threads);
+  return NULL;
+}
+static void extend_mt(const orc_tree* t, const fe* evals, size_t n, int moiety, fe* out, int threads) {
+  if (threads <= 1 || n <= 2048) {
+    extend_impl(t, evals, n, moiety, out, 0);
+    return;
+  }
+  unsigned layer = (ilog2(2 * t->n) - 2) - ilog2(n);
+  size_t layer_size = (t->n / 2) >> layer;
+  size_t h = n / 2;
+  fe *e0 = fe_alloc(h), *e1 = fe_alloc(h), *e0p = fe_alloc(h), *e1p = fe_alloc(h);
+  bf_ctx d = {t->dmat + 4 * layer_size, moiety == 0 ? 1 : 0, evals, evals + h, e0, e1};
+  parallel_for(h, threads, bf_range, &d);
+  pthread_t th;
+  mt_job j = {t, e0, h, moiety, e0p, threads / 2};
+  pthread_create(&th, NULL, extend_mt_thread, &j);
+  extend_mt(t, e1, h, moiety, e1p, threads - threads / 2);
+  pthread_join(th, NULL);
+  bf_ctx r = {t->rmat + 4 * layer_size, moiety == 1 ? 1 : 0, e0p, e1p, out, out + h};
+  parallel_for(h, threads, bf_range, &r);
+  free(e0); free(e1); free(e0p); free(e1p);
+}
+typedef struct { const fe *u0, *v0, *u1, *v1, *xnn; fe* out; } cb_ctx;
+static void cb_range(size_t lo, size_t hi, void* p) {
+  cb_ctx* c = (cb_ctx*)p;
+  for (size_t i = lo; i < hi; i++) {
+    fe m;
+    fe_mul(&m, &c->v0[i], &c->xnn[2 * i]);
+    fe_add(&c->out[2 * i], &c->u0[i], &m);
+    fe_mul(&m, &c->v1[i], &c->xnn[2 * i + 1]);
+    fe_add(&c->out[2 * i + 1], &c->u1[i], &m);
+  }
+}
+static void enter_mt(const orc_tree* t, const fe* coeffs, size_t n, fe* out, int threads);
+static void* enter_mt_thread(void* p) {
+  mt_job* j = (mt_job*)p;
+  enter_mt(j->t, j->in, j->n, j->out, j->threads);
+  return NULL;
+}
+static void enter_mt(const orc_tree* t, const fe* coeffs, size_t n, fe* out, int threads) {
+  if (threads <= 1 || n <= 2048) {
+    enter_impl(t, coeffs, n, out, 0);
+    return;
+  }
+  size_t h = n / 2;
+  fe *u0 = fe_alloc(h), *v0 = fe_alloc(h), *u1 = fe_alloc(h), *v1 = fe_alloc(h);
+  pthread_t th;
+  mt_job j = {t->sub, coeffs, h, 0, u0, threads / 2};
+  pthread_create(&th, NULL, enter_mt_thread, &j);
+  enter_mt(t->sub, coeffs + h, h, v0, threads - threads / 2);
+  pthread_join(th, NULL);
+  mt_job e = {t, u0, h, 1, u1, threads / 2};
+  pthread_create(&th, NULL, extend_mt_thread, &e);
+  extend_mt(t, v0, h, 1, v1, threads - threads / 2);
+  pthread_join(th, NULL);
+  cb_ctx c = {u0, v0, u1, v1, t->xnn_s, out};
+  parallel_for(h, threads, cb_range, &c);
+  free(u0); free(v0); free(u1); free(v1);
+}
 int orc_enter_mt(const orc_tree* t, const fe* coeffs, size_t n, fe* out, int threads) {
   const orc_tree* s = orc_subtree_with_size(t, n);
   if (!s) return 1;
-  int depth = 0;
-  while ((1 << (depth + 1)) <= threads) depth++;
-  enter_impl(s, coeffs, n, out, depth);
+  enter_mt(s, coeffs, n, out, threads < 1 ? 1 : threads);
   return 0;
 }
+
 /* Bottom-up restatement of enter_impl for the recursion depths m_lo < m <= m_hi: `in` holds n/m_lo
  * evaluation vectors of length m_lo (m_lo = 1: coefficients); after the pass for m it holds n/m vectors
  * of length m.  orc_enter_range(t, c, n, 1, n, out) == orc_enter(t, c, n, out); used to check the flat
