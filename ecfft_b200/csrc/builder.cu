@@ -118,25 +118,68 @@ Tree* tree_from_leaves(const Fp* leaves_dev_plain, size_t n, const std::vector<R
   return t;
 }
 
-// Normalised-butterfly tables of chain level k (DESIGN.md "twiddle form"), derived from the top
-// tree's f and the level's recombine matrices.
+// Symmetric butterflies need every rational map in the form (x^2 + c1 x + c0)/x with c0 = beta^2 a
+// nonzero square (the Good-curve 2-isogenies of src/ec.rs:84 are (x - b)^2/x): then the two nodes of
+// a pair are s and beta^2/s.  Fills t.beta / t.sym_ok.
+static void find_betas(Tree& t) {
+  t.beta.clear();
+  t.sym_ok = false;
+  Fp two = fp_add(fp_one(), fp_one()), inv2 = fp_inv(two);
+  for (const RatMapHost& m : t.maps) {
+    if (m.den.size() != 2 || !fp_is_zero(m.den[0]) || !fp_eq(m.den[1], fp_one())) return;
+    if (m.num.size() != 3 || !fp_eq(m.num[2], fp_one()) || fp_is_zero(m.num[0])) return;
+    Fp beta = fp_mul(fp_neg(m.num[1]), inv2);
+    if (!fp_eq(fp_sqr(beta), m.num[0])) {
+      beta = fp_sqrt_candidate(m.num[0]);
+      if (!fp_eq(fp_sqr(beta), m.num[0])) return;
+    }
+    t.beta.push_back(beta);
+  }
+  t.sym_ok = true;
+}
+
+// Normalised-butterfly tables of chain level k, derived from the top tree's f and the
+// level's recombine matrices: symmetric form when the maps allow it, else the two-product form.
 void build_norm_tables(Tree& t, uint32_t k) {
   if (k == 0) return;
+  if (t.beta.size() != t.maps.size()) find_betas(t);
   const size_t n = t.n(), N = (size_t)1 << k, stride = n / N, hh = N / 2;
   cudaStream_t st = t.stream;
   Level& lv = t.levels[k];
+  lv.sym = t.sym_ok && k::butterfly_mode() == 2;
+  Fp* beta_dev = nullptr;
+  Fp inv2L = fp_one();
+  if (lv.sym) {
+    // level with half-stride 2^j uses map k-2-j (the layer with 2^(j+2) nodes)
+    std::vector<Fp> bj(k > 1 ? k - 1 : 1, fp_zero());
+    Fp inv2 = fp_inv(fp_add(fp_one(), fp_one()));
+    for (uint32_t j = 0; j + 1 < k; j++) {
+      bj[j] = t.beta[k - 2 - j];
+      inv2L = fp_mul(inv2L, inv2);
+    }
+    beta_dev = t.dalloc(bj.size());
+    ECFFT_CUDA(cudaMemcpyAsync(beta_dev, bj.data(), bj.size() * sizeof(Fp), cudaMemcpyHostToDevice, st));
+    ECFFT_CUDA(cudaStreamSynchronize(st));
+  }
+  const size_t per = lv.sym ? 1 : 2;
   for (int mu = 0; mu < 2; mu++) {
-    lv.tw_r[mu] = t.dalloc(2 * hh);
-    lv.tw_d[mu] = t.dalloc(2 * hh);
-    k::build_twiddles(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, st);
+    lv.tw_r[mu] = t.dalloc(per * hh);
+    lv.tw_d[mu] = t.dalloc(per * hh);
     lv.gam[mu] = t.dalloc(hh);
     lv.gami[mu] = t.dalloc(hh);
-    k::build_gamma(lv.gam[mu], lv.rmat, hh, mu, st);
+    if (lv.sym) {
+      k::build_twiddles_sym(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, beta_dev, st);
+      k::build_gamma_sym(lv.gam[mu], lv.rmat, t.f, stride, hh, mu, beta_dev, st);
+    } else {
+      k::build_twiddles(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, st);
+      k::build_gamma(lv.gam[mu], lv.rmat, hh, mu, st);
+    }
     ECFFT_CUDA(cudaMemcpyAsync(lv.gami[mu], lv.gam[mu], hh * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     k::batch_inverse(lv.gami[mu], hh, st);
-#ifndef ECFFT_D_DIFFFORM
-    k::fold_sumform_prescale(lv.gami[mu], t.f, stride, hh, mu, st);
-#endif
+    if (lv.sym)
+      k::mul_const(lv.gami[mu], lv.gami[mu], inv2L, hh, st);  // the decompose butterflies omit their 1/2
+    else
+      k::fold_sumform_prescale(lv.gami[mu], t.f, stride, hh, mu, st);
   }
   lv.gx = t.dalloc(hh);
   k::mul_strided(lv.gx, lv.gam[1], lv.xnn_s, 2, 1, hh, st);

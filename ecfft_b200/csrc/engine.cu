@@ -64,19 +64,6 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
   Fp* ping[2] = {nullptr, nullptr};
   const Fp* cur = in;
   uint32_t idx = 0;
-  // depths with block size <= 1024 run fused in shared memory (k_enter_small)
-  if (m_lo < 1024 && getenv("ECFFT_B200_SMALL_FUSION")) {  // opt-in: measured no faster (profiles/r01_f_*)
-    const size_t m_small = m_hi < 1024 ? m_hi : 1024;
-    Fp* dst = (m_small == m_hi && out != in) ? out : (ping[0] = tmp(n));
-    if (k::enter_small(t.levels.data(), cur, dst, n, m_lo, m_small, st)) {
-      cur = dst;
-      m_lo = m_small;
-      idx = 1;
-    } else if (ping[0]) {
-      release(ping[0]);
-      ping[0] = nullptr;
-    }
-  }
   for (size_t m = m_lo * 2; m <= m_hi; m *= 2, idx++) {
     const Level& lv = level_for(m);
     const size_t h = m / 2;
@@ -89,7 +76,7 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
     }
     // u1, v1 for every block at once; with the normalised tables the Gamma^1 scaling of the
     // EXTEND output is folded into the combine
-    const bool unscaled = k::butterfly_mode() == 1 && lv.gx && lv.gam[1] && lv.tw_r[1] && lv.tw_d[0] && lv.gami[0];
+    const bool unscaled = k::butterfly_mode() != 0 && lv.has_norm();
     k::extend(lv, cur, W, ilog2(h), n / h, S1, st, unscaled);
     k::enter_combine(lv, cur, W, dst, ilog2(h), n, unscaled, st);
     cur = dst;

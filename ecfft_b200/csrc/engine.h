@@ -61,11 +61,18 @@ struct Level {
   bool has_z = false;       // z tables present (full build)
   // Normalised-butterfly tables (DESIGN.md "twiddle form"), derived from f and rmat; h = N/2.
   // Index (2^j + i) addresses butterfly i of the level with half-stride 2^j; moiety mu = 0/1.
-  Fp* tw_r[2] = {nullptr, nullptr};   // h entries of {s0, s1}: the two tree nodes the pair maps through
-  Fp* tw_d[2] = {nullptr, nullptr};   // h entries of {1/(s1-s0), -s0}
+  // sym = false ("normalised", 2 products per pair): tw_r = {s0, s1} (the two tree nodes of the pair),
+  //   tw_d = {-s1, -s0}, 2 Fp per butterfly; gami also carries the sum-form input scalings.
+  // sym = true ("symmetric", 1 product per pair; maps of the form (x^2 + c1 x + beta^2)/x):
+  //   tw_r = g = (s0 - beta)/(s0 + beta), tw_d = 1/g, 1 Fp per butterfly; gam = prod_j (s + beta_j) v_j(s),
+  //   gami = 2^-L / gam.
+  bool sym = false;
+  Fp* tw_r[2] = {nullptr, nullptr};
+  Fp* tw_d[2] = {nullptr, nullptr};
   Fp* gam[2] = {nullptr, nullptr};    // h: accumulated scale Gamma^mu_p of the recombine network
-  Fp* gami[2] = {nullptr, nullptr};   // h: 1/Gamma^mu_p
+  Fp* gami[2] = {nullptr, nullptr};   // h: pre-scale of the decompose network (1/Gamma^mu_p and folded constants)
   Fp* gx = nullptr;                   // h: Gamma^1_i * xnn_s[2i+1] (ENTER combine)
+  bool has_norm() const { return tw_r[0] && tw_r[1] && tw_d[0] && tw_d[1] && gam[0] && gam[1] && gami[0] && gami[1] && gx; }
 };
 
 struct RatMapHost {  // reference utils.rs:367-371; coefficients low->high, plain canonical
@@ -80,6 +87,8 @@ struct Tree {
   Fp* f = nullptr;                   // top-level BinaryTree<F>, 2n entries (f[0] = 0)
   std::vector<Level> levels;         // levels[k] has 2^k leaves, k = 0..log_n
   std::vector<RatMapHost> maps;      // log_n rational maps (level k uses the first k)
+  std::vector<Fp> beta;              // per map: fixed point of its deck involution x -> beta^2/x (symmetric butterflies)
+  bool sym_ok = false;               // every map is (x^2 + c1 x + beta^2)/x
   int parts = PARTS_FULL;
   Fp base_leaf0, base_leaf1;         // leaves of the 2-leaf chain level (VANISH base case, fftree.rs:293-298)
   cudaStream_t stream = nullptr;     // default stream for host-buffer calls
@@ -110,12 +119,10 @@ namespace k {
 // the final Gamma scaling to the caller (ENTER folds it into its combine).
 void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st,
             bool unscaled_out = false);
-// all ENTER depths m_lo < m <= m_hi <= 1024 in one shared-memory kernel; false if unavailable
-bool enter_small(const Level* levels, const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, cudaStream_t st);
 void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st);
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
 void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st);
-int butterfly_mode();  // 1 = normalised (default), 0 = 2x2 matrices (ECFFT_B200_BUTTERFLY=matrix)
+int butterfly_mode();  // ECFFT_B200_BUTTERFLY: 2 = symmetric (default), 1 = normalised, 0 = 2x2 matrices
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
 // scaling (lv.gam[1], lv.gx are used instead of xnn's odd entries).
 void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t log_h, size_t n, bool W_unscaled, cudaStream_t st);
@@ -153,6 +160,9 @@ void build_matrices(Fp* rmat_layer, Fp* dmat_layer, const Fp* flayer, size_t fst
 void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
 void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st);
 void fold_sumform_prescale(Fp* gami, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
+// symmetric-form tables; beta_by_j[j] is the fixed point of the map used by the level with half-stride 2^j
+void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st);
+void build_gamma_sym(Fp* gam, const Fp* rmat, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st);
 void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st);  // out[i] = a[i]*b[b_off + i*b_stride]
 }  // namespace k
 

@@ -252,6 +252,28 @@ FP_HD Fp fp_sub_lazy(const Fp& a, const Fp& b) {
   return r;
 }
 
+// a - b mod p for lazy a AND lazy b in [0,2^256); lazy result.  a - b = d - borrow*2^256 with
+// d the wrapped difference, and 2^256 = DELTA (mod p): subtract DELTA once per borrow.  The first
+// correction can borrow again only when d < DELTA; the wrapped value then lies in
+// [2^256 - DELTA, 2^256), whose limbs >= 2 are all ones and whose low 64 bits exceed 2*DELTA,
+// so the second correction touches two limbs and cannot borrow.
+FP_HD Fp fp_sub_lazy2(const Fp& a, const Fp& b) {
+  Fp d;
+  d.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) d.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t b1 = subc(0u, 0u);  // 0 or 0xFFFFFFFF
+  Fp r;
+  r.v[0] = sub_cc(d.v[0], b1 & FP_C977);
+  r.v[1] = subc_cc(d.v[1], b1 & 1u);
+#pragma unroll
+  for (int i = 2; i < 8; i++) r.v[i] = subc_cc(d.v[i], 0u);
+  uint32_t b2 = subc(0u, 0u);
+  r.v[0] = sub_cc(r.v[0], b2 & FP_C977);
+  r.v[1] = subc(r.v[1], b2 & 1u);
+  return r;
+}
+
 // ---------------------------------------------------------------------------
 // 512(+1)-bit product accumulator, split into an even-aligned and an
 // odd-aligned half so every partial product lands on a 64-bit-aligned limb

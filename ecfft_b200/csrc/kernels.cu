@@ -388,23 +388,34 @@ void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, 
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st) {
   const Fp* table = phase == 0 ? lv.tw_d[0] : lv.tw_r[1];
   if (!table) throw Error(ERR_MISSING_TABLES, "mg_cross: normalised tables missing");
-  const Fp* layer = table + 2 * ((size_t)1 << j);
   const size_t mask = ((size_t)1 << j) - 1, ibase = p_pos0 & mask;
+  if (lv.sym) {  // symmetric form: one twiddle per pair
+    const Fp* layer = table + ((size_t)1 << j);
+    map(count, st, [=] __device__(size_t e) {
+      Fp g = fp_load_ro(layer + ((ibase + e) & mask));
+      Fp xo = fp_load(own + e), xr = fp_load(partner + e);
+      Fp xp = role == 0 ? xo : xr, xq = role == 0 ? xr : xo;
+      Fp res;
+      if (phase == 0)  // decompose: x_p = y_p + y_q, x_q = (y_p - y_q)/g
+        res = role == 0 ? fp_add_lazy(xp, xq) : fp_mul_lazy(g, fp_sub_lazy2(xp, xq));
+      else {           // recombine: y_p = x_p + g x_q, y_q = x_p - g x_q
+        Fp t = fp_mul_lazy(g, xq);
+        res = role == 0 ? fp_add_lazy(xp, t) : fp_sub_lazy2(xp, t);
+      }
+      fp_store(out + e, fp_canon(res));
+    });
+    return;
+  }
+  const Fp* layer = table + 2 * ((size_t)1 << j);
   map(count, st, [=] __device__(size_t e) {
     const Fp* tw = layer + 2 * ((ibase + e) & mask);
     Fp xo = fp_load(own + e), xr = fp_load(partner + e);
     Fp xp = role == 0 ? xo : xr, xq = role == 0 ? xr : xo;
     Fp res;
-    if (phase == 0) {
-#ifndef ECFFT_D_DIFFFORM   // decompose, sum form: y_q = x^_p + x^_q, y_p = -(s1 x^_p + s0 x^_q)
+    if (phase == 0)    // decompose, sum form: y_q = x^_p + x^_q, y_p = -(s1 x^_p + s0 x^_q)
       res = role == 1 ? fp_add_lazy(xp, xq) : fp_dot2_lazy(fp_load_ro(tw), xp, fp_load_ro(tw + 1), xq);
-#else                    // decompose: y_q = c (x_q - x_p), y_p = x_p - s0 y_q
-      Fp yq = fp_mul_lazy(fp_load_ro(tw), fp_sub_lazy(xq, fp_canon(xp)));
-      res = role == 1 ? yq : fp_muladd_lazy(xp, fp_load_ro(tw + 1), yq);
-#endif
-    } else {           // recombine: y_p = x_p + s0 x_q, y_q = x_p + s1 x_q
+    else               // recombine: y_p = x_p + s0 x_q, y_q = x_p + s1 x_q
       res = fp_muladd_lazy(xp, fp_load_ro(tw + role), xq);
-    }
     fp_store(out + e, fp_canon(res));
   });
 }
@@ -436,13 +447,8 @@ void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t 
     Fp s1 = fp_load(f_top + (2 * B + 2 * i + mu + B) * fstride);
     fp_store(tw_r + 2 * idx, s0);
     fp_store(tw_r + 2 * idx + 1, s1);
-#ifndef ECFFT_D_DIFFFORM
     fp_store(tw_d + 2 * idx, fp_neg(s1));
     fp_store(tw_d + 2 * idx + 1, fp_neg(s0));
-#else
-    fp_store(tw_d + 2 * idx, fp_inv(fp_sub(s1, s0)));
-    fp_store(tw_d + 2 * idx + 1, fp_neg(s0));
-#endif
   });
 }
 // Sum-form decompose: fold the per-level input scalings (-c for the lower, +c for the upper element of
@@ -471,6 +477,40 @@ void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st) {
     for (uint32_t j = 0; ((size_t)1 << j) < h; j++) {
       size_t i = p & (((size_t)1 << j) - 1), b = (p >> j) & 1;
       acc = fp_mul_lazy(acc, fp_load(rmat + 4 * (((size_t)2 << j) + 2 * i + mu) + 2 * b));
+    }
+    fp_store(gam + p, fp_canon(acc));
+  });
+}
+// Symmetric-form tables (DESIGN.md 4.1 "symmetric"): the level's map x -> (x^2 + c1 x + beta^2)/x
+// identifies s with beta^2/s, and g(s) = (s - beta)/(s + beta) takes opposite values on the two.
+// Entry idx = 2^j + i holds g(s0) resp. 1/g(s0) for s0 = the pair's lower node.
+void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t idx) {
+    if (idx == 0) {
+      fp_store(tw_r, fp_zero());
+      fp_store(tw_d, fp_zero());
+      return;
+    }
+    uint32_t j = 63 - __clzll((unsigned long long)idx);
+    size_t i = idx - ((size_t)1 << j), B = (size_t)2 << j;
+    Fp s0 = fp_load(f_top + (2 * B + 2 * i + mu) * fstride);
+    Fp b = fp_load_ro(beta_by_j + j);
+    Fp nu = fp_sub(s0, b), de = fp_add(s0, b);
+    Fp t = fp_inv(fp_mul(nu, de));
+    fp_store(tw_r + idx, fp_mul(fp_mul(nu, nu), t));
+    fp_store(tw_d + idx, fp_mul(fp_mul(de, de), t));
+  });
+}
+// Gamma^mu_p = prod_j (s + beta_j) v(s)^(2^j - 1) over the nodes s the position passes through; the v
+// powers are the first-column entries of the recombine matrices as in build_gamma.
+void build_gamma_sym(Fp* gam, const Fp* rmat, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t p) {
+    Fp acc = fp_one();
+    for (uint32_t j = 0; ((size_t)1 << j) < h; j++) {
+      size_t i = p & (((size_t)1 << j) - 1), b = (p >> j) & 1, B = (size_t)2 << j;
+      Fp s = fp_load(f_top + (2 * B + 2 * i + mu + b * B) * fstride);
+      acc = fp_mul_lazy(acc, fp_load(rmat + 4 * (B + 2 * i + mu) + 2 * b));
+      acc = fp_mul_lazy(acc, fp_add(s, fp_load_ro(beta_by_j + j)));
     }
     fp_store(gam + p, fp_canon(acc));
   });

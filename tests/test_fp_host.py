@@ -78,6 +78,12 @@ def test_add_sub_mont(shim):
         lazy = rnd(r)                                # any 256-bit pattern minus a canonical value
         shim.fph_sub_lazy(enc(lazy), enc(b), out)
         assert dec(out) % P == (lazy - b) % P
+        shim.fph_sub_lazy2(enc(l1), enc(l2), out)   # lazy - lazy (the one-multiplication butterfly)
+        assert dec(out) % P == (l1 - l2) % P
+        small = r.getrandbits(r.choice([4, 20, 33]))  # a - b just below -p: the double-borrow path
+        big = 2**256 - 1 - r.getrandbits(r.choice([2, 20, 33]))
+        shim.fph_sub_lazy2(enc(small), enc(big), out)
+        assert dec(out) % P == (small - big) % P
         shim.fph_mont_mul(enc(a), enc(b), out)      # the CIOS Montgomery alternative (a*b*R^-1)
         assert dec(out) == a * b * rinv % P
 

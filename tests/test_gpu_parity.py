@@ -217,9 +217,11 @@ def test_tree_new_from_leaves(oracle_mod):
         eq(t.table(name), ref.table(ORACLE_NAMES.get(name, name)))
 
 
-def test_matrix_butterfly_mode_matches_too():
+@pytest.mark.parametrize("mode", ["matrix", "normalised"])
+def test_other_butterfly_modes_match_too(mode):
     """ECFFT_B200_BUTTERFLY=matrix selects the reference-shaped 2x2 mat-vec butterflies (the measured
-    'phase 1' kernel); both modes must give the oracle's bits."""
+    'phase 1' kernel), =normalised the two-product twiddle form (also the fallback for trees whose maps are
+    not (x^2 + c1 x + beta^2)/x); the default is the one-product symmetric form.  All give the oracle's bits."""
     import os
     import subprocess
     import sys
@@ -232,8 +234,9 @@ def test_matrix_butterfly_mode_matches_too():
         "assert (g.enter(x) == c.enter(x)).all()\n"
         "assert (g.exit(x) == c.exit(x)).all()\n"
         "assert (g.extend(x[:n//2], 0) == c.extend(x[:n//2], 0)).all()\n"
+        "assert (g.mextend(x[:n//2], 1) == c.mextend(x[:n//2], 1)).all()\n"
         "print('matrix mode ok')\n")
-    env = dict(os.environ, ECFFT_B200_BUTTERFLY="matrix")
+    env = dict(os.environ, ECFFT_B200_BUTTERFLY=mode)
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0 and "matrix mode ok" in r.stdout, r.stdout + r.stderr

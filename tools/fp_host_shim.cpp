@@ -24,3 +24,4 @@ void fph_consts(uint32_t* R, uint32_t* RINV) { Fp a = fp_const_R(), b = fp_const
 extern "C" void fph_sqrt(const uint32_t* a, uint32_t* r) { Fp x; memcpy(&x, a, 32); Fp z = fp_sqrt_candidate(x); memcpy(r, &z, 32); }
 extern "C" void fph_sub_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_sub_lazy(x, y); memcpy(r, &z, 32); }
 extern "C" void fph_add_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_add_lazy(x, y); memcpy(r, &z, 32); }
+extern "C" void fph_sub_lazy2(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_sub_lazy2(x, y); memcpy(r, &z, 32); }
