@@ -274,6 +274,48 @@ FP_HD Fp fp_sub_lazy2(const Fp& a, const Fp& b) {
   return r;
 }
 
+// Short forms of fp_add_lazy / fp_sub_lazy2 for the butterfly kernels: the DELTA correction is applied
+// to the low two limbs only and the (probability ~2^-31) carry/borrow out of them takes a branch.
+FP_HD Fp fp_add_lazy_f(const Fp& a, const Fp& b) {
+  Fp s;
+  s.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) s.v[i] = addc_cc(a.v[i], b.v[i]);
+  uint32_t c = addc(0u, 0u);
+  s.v[0] = add_cc(s.v[0], (0u - c) & FP_C977);
+  s.v[1] = addc_cc(s.v[1], c);
+  uint32_t c2 = addc(0u, 0u);
+  if (c2) {  // ripple into the high limbs; a second wrap leaves a tiny value that takes one more DELTA
+    s.v[2] = add_cc(s.v[2], 1u);
+#pragma unroll
+    for (int i = 3; i < 8; i++) s.v[i] = addc_cc(s.v[i], 0u);
+    uint32_t c3 = addc(0u, 0u);
+    s.v[0] = add_cc(s.v[0], (0u - c3) & FP_C977);
+    s.v[1] = addc_cc(s.v[1], c3);
+    s.v[2] = addc(s.v[2], 0u);
+  }
+  return s;
+}
+FP_HD Fp fp_sub_lazy2_f(const Fp& a, const Fp& b) {
+  Fp d;
+  d.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) d.v[i] = subc_cc(a.v[i], b.v[i]);
+  uint32_t b1 = subc(0u, 0u);  // 0 or 0xFFFFFFFF
+  d.v[0] = sub_cc(d.v[0], b1 & FP_C977);
+  d.v[1] = subc_cc(d.v[1], b1 & 1u);
+  uint32_t b2 = subc(0u, 0u);
+  if (b2) {  // borrow ripples through the high limbs; if it falls off the top, one more DELTA (cannot borrow)
+    d.v[2] = sub_cc(d.v[2], 1u);
+#pragma unroll
+    for (int i = 3; i < 8; i++) d.v[i] = subc_cc(d.v[i], 0u);
+    uint32_t b3 = subc(0u, 0u);
+    d.v[0] = sub_cc(d.v[0], b3 & FP_C977);
+    d.v[1] = subc(d.v[1], b3 & 1u);
+  }
+  return d;
+}
+
 // ---------------------------------------------------------------------------
 // 512(+1)-bit product accumulator, split into an even-aligned and an
 // odd-aligned half so every partial product lands on a 64-bit-aligned limb

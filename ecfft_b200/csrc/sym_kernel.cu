@@ -1,0 +1,379 @@
+// sm_100a EXTEND kernel for the symmetric (one-product) butterflies — the dominant kernel of the
+// engine — with ENTER's combine (reference src/fftree.rs:155-159) fused into its last pass.
+// See DESIGN.md 4.1.
+//
+// Butterfly network of EXTEND (flattening of extend_impl, src/fftree.rs:72-120): log2(h) decompose
+// levels (half-strides h/2 .. 1) then log2(h) recombine levels (1 .. h/2), in place, natural order.
+// With g = (s - beta)/(s + beta) the two nodes of a pair carry +g and -g, so a recombine butterfly is
+// y_p = x_p + g x_q, y_q = x_p - g x_q and a decompose butterfly x_p = y_p + y_q, x_q = (y_p - y_q)/g
+// (halvings and the diagonal Gamma scalings folded into one pre- and one post-scale per element).
+//
+// A CTA owns a tile of 2^log_t elements closed under a group of consecutive levels, kept in shared
+// memory (low and high 16 bytes of the elements in separate arrays: conflict-free 16-byte accesses).
+// A thread takes FOUR elements into registers and runs two levels on them (four at the centre of the
+// inner pass: decompose 1, 0 then recombine 0, 1) per shared-memory round trip.  The tile arrives by
+// cp.async (no registers held across the HBM latency); the pre-scale is applied by the first stage as
+// it reads the tile, the post-scale and the canonical reduction by the last stage, which stores to
+// global memory directly — or, in ENTER, leaves the extended values in shared memory for the combine
+// epilogue  out[2i] = u0[i] + v0[i] xnn[2i],  out[2i+1] = gam[i] u1[i] + gx[i] v1[i],
+// for which a tile holds the same positions of the two sibling vectors u and v.
+#include <cstdlib>
+
+#include "engine.h"
+
+namespace ecfft {
+namespace k {
+
+struct SymParams {
+  const Fp* in;
+  Fp* out;
+  const Fp* tw_d;   // 1/g of the source moiety, entry 2^j + i
+  const Fp* tw_r;   // g of the target moiety
+  const Fp* pre;    // per-position scale applied by the first stage (or null)
+  const Fp* post;   // per-position scale applied by the last stage (or null); ignored when comb != 0
+  const Fp* A;      // combine epilogue: the unscaled input vectors [u0 | v0] per block
+  const Fp* xnn;
+  const Fp* gam;
+  const Fp* gx;
+  unsigned long long nv;      // strided: vectors (pair: vector pairs) in the batch; blocks are ordered batch-major
+  unsigned long long total;   // elements in the batch (guards the ragged tile of tiny inputs)
+  uint32_t log_h, log_t;
+  uint32_t lvl_lo, lvl_hi;    // this pass runs the levels lvl_lo <= j < lvl_hi
+  uint32_t boff;              // tile-index bit of level j is j + boff (mod 2^32)
+  uint32_t packed;            // 1: tile = 2^log_t consecutive elements (whole vectors, or a slice of one: inner pass)
+  uint32_t log_c, krows, row_shift;  // strided: 2^krows rows of 2^log_c contiguous elements, rows 2^row_shift apart
+  uint32_t pair;              // strided: top tile bit selects vector 2w / 2w+1
+  uint32_t comb;              // 1: combine epilogue
+  uint32_t do_d, do_r;
+};
+
+enum : uint32_t { OP_D_HI = 1, OP_D_LO = 2, OP_R_LO = 4, OP_R_HI = 8 };
+
+struct TileSoA {
+  uint4* s;
+  uint32_t T;
+  __device__ __forceinline__ Fp ld(uint32_t e) const {
+    uint4 a = s[e], b = s[T + e];
+    Fp r;
+    r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+    r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+    return r;
+  }
+  __device__ __forceinline__ void st(uint32_t e, const Fp& x) const {
+    s[e] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);
+    s[T + e] = make_uint4(x.v[4], x.v[5], x.v[6], x.v[7]);
+  }
+};
+
+__device__ __forceinline__ void sym_d_pair(Fp& a, Fp& b, const Fp& ginv) {  // x_p = y_p + y_q, x_q = (y_p - y_q)/g
+  Fp d = fp_sub_lazy2_f(a, b);
+  a = fp_add_lazy_f(a, b);
+  b = fp_mul_lazy(ginv, d);
+}
+__device__ __forceinline__ void sym_r_pair(Fp& a, Fp& b, const Fp& g) {     // y_p = x_p + g x_q, y_q = x_p - g x_q
+  Fp t = fp_mul_lazy(g, b);
+  b = fp_sub_lazy2_f(a, t);
+  a = fp_add_lazy_f(a, t);
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+// tile element -> (offset from the tile's first global element, position within its vector)
+struct TileMap {
+  uint32_t log_c, cmask, rmask, krows, row_shift, log_h, pos0;
+  __device__ __forceinline__ void map(uint32_t e, unsigned long long& goff, uint32_t& pos) const {
+    const uint32_t rr = e >> log_c, c = e & cmask;
+    const uint32_t rel = ((rr & rmask) << row_shift) + c;
+    pos = pos0 + rel;
+    goff = ((unsigned long long)(rr >> krows) << log_h) + rel;
+  }
+};
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__ SymParams p) {
+  extern __shared__ uint4 smem_raw[];
+  const uint32_t T = 1u << p.log_t;
+  const TileSoA s{smem_raw, T};
+  const uint32_t hmask = (1u << p.log_h) - 1;
+  TileMap tm;
+  unsigned long long gbase;
+  if (p.packed) {
+    tm = TileMap{p.log_t, T - 1, 0u, 0u, 0u, p.log_h, 0u};
+    gbase = (unsigned long long)blockIdx.x << p.log_t;
+  } else {
+    const unsigned long long w = blockIdx.x % p.nv;
+    const unsigned long long tile = blockIdx.x / p.nv;
+    const uint32_t ncg_log = p.row_shift - p.log_c;
+    const uint32_t cg = (uint32_t)(tile & ((1ull << ncg_log) - 1));
+    const uint32_t q_hi = (uint32_t)(tile >> ncg_log);
+    const uint32_t pos0 = (q_hi << p.lvl_hi) + (cg << p.log_c);  // position within the vector of tile element 0
+    tm = TileMap{p.log_c, (1u << p.log_c) - 1, (1u << p.krows) - 1, p.krows, p.row_shift, p.log_h, pos0};
+    gbase = ((p.pair ? 2 * w : w) << p.log_h) + pos0;
+  }
+
+  // ---- tile load: cp.async straight into the split shared-memory layout
+  for (uint32_t e = threadIdx.x; e < T; e += NT) {
+    unsigned long long goff;
+    uint32_t pos;
+    tm.map(e, goff, pos);
+    const unsigned long long g = gbase + goff;
+    if (g < p.total) {
+      const uint4* src = reinterpret_cast<const uint4*>(p.in + g);
+      cp_async16(&s.s[e], src);
+      cp_async16(&s.s[T + e], src + 1);
+    } else {
+      s.st(e, fp_zero());
+    }
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  __syncthreads();
+
+  // ---- stage schedule (see the header comment of quad stages below)
+  const uint32_t nlev = p.lvl_hi - p.lvl_lo;
+  const bool mid = p.do_d && p.do_r && nlev >= 2;       // levels lvl_lo+1, lvl_lo run D, D, R, R in one stage
+  const uint32_t j_base = p.lvl_lo + (mid ? 2 : 0);     // lowest level of the plain D / R stages
+  const uint32_t cnt = p.lvl_hi - j_base, odd = cnt & 1, npairs = cnt >> 1;
+  const uint32_t nD = p.do_d ? odd + npairs : 0, nR = p.do_r ? odd + npairs : 0;
+  const uint32_t nstages = nD + (mid ? 1 : 0) + nR;
+
+  for (uint32_t sidx = 0; sidx < nstages; sidx++) {
+    // The quad of item q differs in tile-index bits b_lo (level jl) and b_hi (level jh); ops selects which
+    // of the level operations run.  When both levels are used jl = jh - 1, so the two low-level pairs
+    // share a twiddle.  Single-level stages (odd level counts) pair bit b_hi only; b_lo is any other bit.
+    uint32_t ops, jh, jl;
+    if (sidx < nD) {
+      if (odd && sidx == 0) { ops = OP_D_HI; jh = p.lvl_hi - 1; jl = 0; }
+      else { const uint32_t u = sidx - odd; ops = OP_D_HI | OP_D_LO; jh = p.lvl_hi - 1 - odd - 2 * u; jl = jh - 1; }
+    } else if (mid && sidx == nD) {
+      ops = OP_D_HI | OP_D_LO | OP_R_LO | OP_R_HI; jh = p.lvl_lo + 1; jl = p.lvl_lo;
+    } else {
+      const uint32_t t = sidx - nD - (mid ? 1 : 0);
+      if (t < npairs) { ops = OP_R_LO | OP_R_HI; jl = j_base + 2 * t; jh = jl + 1; }
+      else { ops = OP_R_HI; jh = p.lvl_hi - 1; jl = 0; }
+    }
+    const bool two = (ops & (OP_D_LO | OP_R_LO)) != 0;
+    const uint32_t b_hi = jh + p.boff;
+    const uint32_t b_lo = two ? jl + p.boff : (b_hi == 0 ? 1u : b_hi - 1);
+    const uint32_t b1 = b_lo < b_hi ? b_lo : b_hi, b2 = b_lo < b_hi ? b_hi : b_lo;
+    const uint32_t S_lo = 1u << b_lo, S_hi = 1u << b_hi;
+    const uint32_t mh = (1u << jh) - 1, ml = (1u << jl) - 1;
+    const bool first = sidx == 0 && p.pre != nullptr;
+    const bool last = sidx + 1 == nstages;
+    const bool to_global = last && !p.comb;
+    const Fp* d_hi = p.tw_d + (1u << jh);
+    const Fp* d_lo = p.tw_d + (1u << jl);
+    const Fp* r_hi = p.tw_r + (1u << jh);
+    const Fp* r_lo = p.tw_r + (1u << jl);
+#pragma unroll 1
+    for (uint32_t q = threadIdx.x; q < T / 4; q += NT) {
+      uint32_t e0 = ((q >> b1) << (b1 + 1)) | (q & ((1u << b1) - 1));     // zero bit at b1
+      e0 = ((e0 >> b2) << (b2 + 1)) | (e0 & ((1u << b2) - 1));            // and at b2
+      const uint32_t e1 = e0 + S_lo, e2 = e0 + S_hi, e3 = e1 + S_hi;
+      unsigned long long g0, g1, g2, g3;
+      uint32_t pa, pb, pc, pd;
+      tm.map(e0, g0, pa);
+      tm.map(e1, g1, pb);
+      tm.map(e2, g2, pc);
+      tm.map(e3, g3, pd);
+      Fp x0 = s.ld(e0), x1 = s.ld(e1), x2 = s.ld(e2), x3 = s.ld(e3);
+      if (first) {
+        x0 = fp_mul_lazy(x0, fp_load_ro(p.pre + (pa & hmask)));
+        x1 = fp_mul_lazy(x1, fp_load_ro(p.pre + (pb & hmask)));
+        x2 = fp_mul_lazy(x2, fp_load_ro(p.pre + (pc & hmask)));
+        x3 = fp_mul_lazy(x3, fp_load_ro(p.pre + (pd & hmask)));
+      }
+      if (ops & OP_D_HI) {
+        sym_d_pair(x0, x2, fp_load_ro(d_hi + (pa & mh)));
+        sym_d_pair(x1, x3, fp_load_ro(d_hi + (pb & mh)));
+      }
+      if (ops & OP_D_LO) {
+        const Fp gi = fp_load_ro(d_lo + (pa & ml));
+        sym_d_pair(x0, x1, gi);
+        sym_d_pair(x2, x3, gi);
+      }
+      if (ops & OP_R_LO) {
+        const Fp g = fp_load_ro(r_lo + (pa & ml));
+        sym_r_pair(x0, x1, g);
+        sym_r_pair(x2, x3, g);
+      }
+      if (ops & OP_R_HI) {
+        sym_r_pair(x0, x2, fp_load_ro(r_hi + (pa & mh)));
+        sym_r_pair(x1, x3, fp_load_ro(r_hi + (pb & mh)));
+      }
+      if (to_global) {
+        if (p.post) {
+          x0 = fp_mul_lazy(x0, fp_load_ro(p.post + (pa & hmask)));
+          x1 = fp_mul_lazy(x1, fp_load_ro(p.post + (pb & hmask)));
+          x2 = fp_mul_lazy(x2, fp_load_ro(p.post + (pc & hmask)));
+          x3 = fp_mul_lazy(x3, fp_load_ro(p.post + (pd & hmask)));
+        }
+        if (gbase + g0 < p.total) fp_store(p.out + gbase + g0, fp_canon(x0));
+        if (gbase + g1 < p.total) fp_store(p.out + gbase + g1, fp_canon(x1));
+        if (gbase + g2 < p.total) fp_store(p.out + gbase + g2, fp_canon(x2));
+        if (gbase + g3 < p.total) fp_store(p.out + gbase + g3, fp_canon(x3));
+      } else {
+        s.st(e0, x0); s.st(e1, x1); s.st(e2, x2); s.st(e3, x3);
+      }
+    }
+    if (!to_global) __syncthreads();
+  }
+
+  if (p.comb) {
+    // ENTER combine (src/fftree.rs:155-159).  The tile holds the unscaled EXTEND of u at element eu and of
+    // v at ev for the same position i; u0, v0 come back from global memory (this CTA's own input
+    // when the whole EXTEND ran in this launch, else the depth's input vector).
+    const uint32_t ush = p.packed ? p.log_h : p.log_t - 1;
+#pragma unroll 1
+    for (uint32_t idx = threadIdx.x; idx < T / 2; idx += NT) {
+      const uint32_t eu = ((idx >> ush) << (ush + 1)) | (idx & ((1u << ush) - 1));
+      const uint32_t ev = eu + (1u << ush);
+      unsigned long long gu, gv;
+      uint32_t pu, pv;
+      tm.map(eu, gu, pu);
+      tm.map(ev, gv, pv);
+      gu += gbase;
+      gv += gbase;
+      if (gv >= p.total) continue;
+      const uint32_t i = pu & hmask;
+      Fp* o = p.out + (gu - i) + 2ull * i;
+      const Fp u0 = fp_load(p.A + gu), v0 = fp_load(p.A + gv);
+      fp_store(o, fp_canon(fp_muladd_lazy(u0, v0, fp_load_ro(p.xnn + 2 * i))));
+      const Fp u1 = s.ld(eu), v1 = s.ld(ev);
+      fp_store(o + 1, fp_canon(fp_dot2_lazy(fp_load_ro(p.gam + i), u1, fp_load_ro(p.gx + i), v1)));
+    }
+  }
+}
+
+// Launch shapes (ECFFT_B200_SYM_VARIANT): 0 = 128 threads, 5 CTAs/SM, 1024-element tile (default);
+// 1 = 128 threads, 4 CTAs/SM; 2 = 256 threads, 3 CTAs/SM; 3 = 256 threads, 2 CTAs/SM, 2048-element tile.
+static int sym_variant() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_SYM_VARIANT");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 3) v = 0;
+  }
+  return v;
+}
+static uint32_t sym_log_tile() { return sym_variant() == 3 ? 11 : 10; }
+
+template <int NT, int MINB>
+static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp))));
+    configured = true;
+  }
+  k_extend_sym<NT, MINB><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
+}
+
+static void launch_sym(const SymParams& p, cudaStream_t st) {
+  const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
+  if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
+  const bool timed = prof::enabled();
+  if (timed) {
+    // algorithmic bytes (level-streaming model of the reference algorithm): every level reads and writes
+    // each element once (64 B) and reads its 2^j matrices (128 B) once; a combine moves 128 B per element
+    const double levels = (double)(p.lvl_hi - p.lvl_lo) * (p.do_d + p.do_r);
+    double mats = 0;
+    for (uint32_t j = p.lvl_lo; j < p.lvl_hi; j++) mats += (double)(p.do_d + p.do_r) * 128.0 * (double)(1ull << j);
+    prof::record_begin(prof::EXTEND_TILE, levels * 64.0 * (double)p.total + mats + (p.comb ? 128.0 * (double)p.total : 0.0), st);
+  }
+  switch (sym_variant()) {
+    case 1: launch_shape<128, 4>(p, tiles, st); break;
+    case 2: launch_shape<256, 3>(p, tiles, st); break;
+    case 3: launch_shape<256, 2>(p, tiles, st); break;
+    default: launch_shape<128, 5>(p, tiles, st); break;
+  }
+  if (timed) prof::record_end(st);
+  prof::count_launch();
+  ECFFT_CUDA(cudaGetLastError());
+}
+
+// All passes of the symmetric EXTEND of nvec vectors of length 2^log_h.  comb != null fuses ENTER's combine
+// into the last pass (nvec even: vectors 2w, 2w+1 are u, v of block w); returns false when this depth
+// cannot be fused (the caller then runs EXTEND and the combine kernel separately).
+bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
+                const SymCombine* comb, cudaStream_t st) {
+  const uint32_t LT = sym_log_tile();
+  const size_t total = nvec << log_h;
+  if (total < 4 || log_h == 0 || log_h > 31) return false;
+  if (comb && (nvec & 1)) return false;
+  SymParams p{};
+  p.tw_d = tw_d;
+  p.tw_r = tw_r;
+  p.total = total;
+  p.log_h = log_h;
+  if (comb) {
+    p.A = comb->A;
+    p.xnn = comb->xnn;
+    p.gam = comb->gam;
+    p.gx = comb->gx;
+  }
+  const uint32_t need = log_h + (comb ? 1 : 0);  // tile bits that hold a whole vector (pair)
+  if (need <= LT) {
+    // whole vectors fit a tile: 2^(log_t-log_h) consecutive vectors per CTA, the entire EXTEND in one launch
+    p.in = in;
+    p.out = comb ? comb->out : out;
+    p.packed = 1;
+    p.log_t = need < 2 ? 2 : need;
+    while (p.log_t < LT && ((size_t)1 << p.log_t) < total) p.log_t++;
+    p.lvl_lo = 0; p.lvl_hi = log_h; p.boff = 0; p.do_d = 1; p.do_r = 1;
+    p.pre = pre;
+    p.post = comb ? nullptr : post;
+    p.comb = comb ? 1 : 0;
+    p.nv = 1;
+    launch_sym(p, st);
+    return true;
+  }
+  if (log_h < LT) return false;                     // only reachable for comb with need == LT + 1
+  const uint32_t outer = log_h - LT;
+  if (comb && outer == 0) return false;             // h == tile: no room for the sibling vector
+  const uint32_t kmax = LT - 5;                     // strided tiles keep rows of >= 32 (pair: 16) contiguous elements
+  const uint32_t npass = (outer + kmax - 1) / kmax;
+  std::vector<uint32_t> bounds;                     // level boundaries from log_h down to LT
+  bounds.push_back(log_h);
+  for (uint32_t i = 1; i <= npass; i++) bounds.push_back(log_h - (outer * i) / npass);
+  p.log_t = LT;
+  const Fp* src = in;
+  for (uint32_t i = 0; i < npass; i++) {            // outer decompose passes, top levels first
+    p.in = src; p.out = out;
+    p.packed = 0; p.pair = 0; p.comb = 0;
+    p.lvl_hi = bounds[i]; p.lvl_lo = bounds[i + 1];
+    p.krows = p.lvl_hi - p.lvl_lo; p.log_c = LT - p.krows; p.row_shift = p.lvl_lo; p.boff = p.log_c - p.lvl_lo;
+    p.nv = nvec;
+    p.do_d = 1; p.do_r = 0;
+    p.pre = i == 0 ? pre : nullptr;
+    p.post = nullptr;
+    launch_sym(p, st);
+    src = out;
+  }
+  // inner pass: all levels below the tile size on contiguous tiles
+  p.in = src; p.out = out;
+  p.packed = 1; p.pair = 0; p.comb = 0; p.nv = 1;
+  p.lvl_lo = 0; p.lvl_hi = LT; p.boff = 0; p.do_d = 1; p.do_r = 1;
+  p.pre = npass == 0 ? pre : nullptr;
+  p.post = npass == 0 ? post : nullptr;
+  launch_sym(p, st);
+  for (uint32_t i = npass; i-- > 0;) {              // outer recombine passes, top levels last
+    const bool fin = i == 0;
+    p.in = out; p.out = (fin && comb) ? comb->out : out;
+    p.packed = 0;
+    p.pair = (fin && comb) ? 1 : 0;
+    p.comb = p.pair;
+    p.lvl_hi = bounds[i]; p.lvl_lo = bounds[i + 1];
+    p.krows = p.lvl_hi - p.lvl_lo; p.log_c = LT - p.pair - p.krows; p.row_shift = p.lvl_lo; p.boff = p.log_c - p.lvl_lo;
+    p.nv = p.pair ? nvec / 2 : nvec;
+    p.do_d = 0; p.do_r = 1;
+    p.pre = nullptr;
+    p.post = (fin && !comb) ? post : nullptr;
+    launch_sym(p, st);
+  }
+  return true;
+}
+
+}  // namespace k
+}  // namespace ecfft

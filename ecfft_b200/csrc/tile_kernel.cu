@@ -172,21 +172,19 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_tile(TileParams p) {
   }
 }
 
-// Launch-shape variants (ECFFT_B200_TILE_VARIANT, measured in profiles/):
+// Launch-shape variants of the radix-2 kernel (ECFFT_B200_TILE_VARIANT, measured in profiles/):
 //   1: 256 threads, 2048-element tile, __launch_bounds__(256, 2)
-//   2: 256 threads, 2048-element tile, __launch_bounds__(256, 3)
 //   7: 128 threads, 1024-element tile, __launch_bounds__(128, 6) — default
-//   11/12/17: as 1/2/7 with the array-of-structures shared-memory layout (2-way bank conflicts)
 static int tile_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ECFFT_B200_TILE_VARIANT");
     v = e ? atoi(e) : 7;
-    if (v != 1 && v != 2 && v != 7 && v != 11 && v != 12 && v != 17) v = 7;
+    if (v != 1 && v != 7) v = 7;
   }
   return v;
 }
-static uint32_t log_tile() { return tile_variant() % 10 == 7 ? 10 : 11; }
+static uint32_t log_tile() { return tile_variant() == 1 ? 11 : 10; }
 
 template <int MODE, int NT, int MINB, bool SOA>
 static void launch_variant(const TileParams& p, size_t tiles, cudaStream_t st) {
@@ -199,14 +197,10 @@ static void launch_variant(const TileParams& p, size_t tiles, cudaStream_t st) {
 }
 template <int MODE>
 static void launch_mode(const TileParams& p, size_t tiles, cudaStream_t st) {
-  switch (tile_variant()) {
-    case 1: launch_variant<MODE, 256, 2, true>(p, tiles, st); break;
-    case 2: launch_variant<MODE, 256, 3, true>(p, tiles, st); break;
-    case 11: launch_variant<MODE, 256, 2, false>(p, tiles, st); break;
-    case 12: launch_variant<MODE, 256, 3, false>(p, tiles, st); break;
-    case 17: launch_variant<MODE, 128, 6, false>(p, tiles, st); break;
-    default: launch_variant<MODE, 128, 6, true>(p, tiles, st); break;
-  }
+  if (tile_variant() == 1)
+    launch_variant<MODE, 256, 2, true>(p, tiles, st);
+  else
+    launch_variant<MODE, 128, 6, true>(p, tiles, st);
 }
 
 static void launch_tile(const TileParams& p, cudaStream_t st) {
@@ -305,12 +299,18 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
   const Moiety source = target == S1 ? S0 : S1;
   const bool norm = lv.has_norm() && butterfly_mode() != 0;
   if (unscaled_out && !norm) throw Error(ERR_INVALID_ARG, "extend: unscaled output needs the normalised tables");
+  const Fp* pre = norm ? lv.gami[source] : nullptr;
+  const Fp* post = (norm && !unscaled_out) ? lv.gam[target] : nullptr;
+  // symmetric butterflies: the radix-4 register-stage kernel (sym_kernel.cu); the radix-2 tile kernel below
+  // remains for the other butterfly forms, for inputs of fewer than 4 elements and ECFFT_B200_SYM_RADIX2
+  static const bool radix2 = getenv("ECFFT_B200_SYM_RADIX2") != nullptr;
+  if (norm && lv.sym && !radix2 && extend_sym(lv.tw_d[source], lv.tw_r[target], in, out, log_h, nvec, pre, post, nullptr, st)) return;
   p.mode = norm ? (lv.sym ? 2 : 1) : 0;
   p.dmat = norm ? lv.tw_d[source] : lv.dmat;
   p.rmat = norm ? lv.tw_r[target] : lv.rmat;
   p.skip_d = target == S0 ? 1 : 0;  // fftree.rs:87-90
   p.skip_r = target == S1 ? 1 : 0;  // fftree.rs:108-111
-  run_passes(p, in, out, log_h, nvec, norm ? lv.gami[source] : nullptr, (norm && !unscaled_out) ? lv.gam[target] : nullptr, st);
+  run_passes(p, in, out, log_h, nvec, pre, post, st);
 }
 
 // Multi-GPU building block: the rank-local levels (half-strides < 2^log_len) of the normalised
@@ -323,6 +323,7 @@ void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaSt
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
   }
+  if (lv.sym && extend_sym(lv.tw_d[0], lv.tw_r[1], in, out, log_len, 1, nullptr, nullptr, nullptr, st)) return;
   TileParams p;
   p.mode = lv.sym ? 2 : 1;
   p.dmat = lv.tw_d[0];

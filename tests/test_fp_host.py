@@ -88,6 +88,35 @@ def test_add_sub_mont(shim):
         assert dec(out) == a * b * rinv % P
 
 
+def test_short_add_sub_rare_paths(shim):
+    """fp_add_lazy_f / fp_sub_lazy2_f (used by the butterfly kernels) correct only the low two limbs and
+    branch on the rare ripple: drive the ripple and double-wrap paths on purpose."""
+    r = random.Random(7)
+    out = A8()
+    M = 2**256
+    for it in range(30000):
+        a = rnd(r)
+        kind = it % 6
+        if kind == 0:      # wrapped sum whose low 64 bits are within DELTA of 2^64: the DELTA fold ripples
+            tgt = (r.getrandbits(192) << 64) | (2**64 - 1 - r.getrandbits(r.choice([3, 20, 33])))
+            b = (tgt + M - a) % M
+        elif kind == 1:    # ... and the high limbs are all ones: double wrap
+            tgt = ((2**192 - 1) << 64) | (2**64 - 1 - r.getrandbits(r.choice([3, 20, 33])))
+            b = (tgt + M - a) % M
+        elif kind == 2:    # a - b borrows and the wrapped difference has low 64 bits below DELTA
+            tgt = (r.getrandbits(192) << 64) | r.getrandbits(r.choice([3, 20, 33]))
+            b = (a - tgt) % M
+        elif kind == 3:    # ... with all-zero high limbs: the borrow falls off the top
+            tgt = r.getrandbits(r.choice([3, 20, 33]))
+            b = (a - tgt) % M
+        else:
+            b = rnd(r)
+        shim.fph_add_lazy_f(enc(a), enc(b), out)
+        assert dec(out) % P == (a + b) % P, (kind, hex(a), hex(b))
+        shim.fph_sub_lazy2_f(enc(a), enc(b), out)
+        assert dec(out) % P == (a - b) % P, (kind, hex(a), hex(b))
+
+
 def test_inverse_sqrt_pow_and_constants(shim):
     r = random.Random(3)
     out = A8()

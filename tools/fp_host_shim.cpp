@@ -25,3 +25,5 @@ extern "C" void fph_sqrt(const uint32_t* a, uint32_t* r) { Fp x; memcpy(&x, a, 3
 extern "C" void fph_sub_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_sub_lazy(x, y); memcpy(r, &z, 32); }
 extern "C" void fph_add_lazy(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_add_lazy(x, y); memcpy(r, &z, 32); }
 extern "C" void fph_sub_lazy2(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_sub_lazy2(x, y); memcpy(r, &z, 32); }
+extern "C" void fph_add_lazy_f(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_add_lazy_f(x, y); memcpy(r, &z, 32); }
+extern "C" void fph_sub_lazy2_f(const uint32_t* a, const uint32_t* b, uint32_t* r) { Fp x, y; memcpy(&x, a, 32); memcpy(&y, b, 32); Fp z = fp_sub_lazy2_f(x, y); memcpy(r, &z, 32); }
