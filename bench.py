@@ -6,8 +6,10 @@
 One JSON line on stdout (rank 0).  A step = one ENTER of n synthetic random coefficients.
   value : evals/s with input and output resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the host-buffer C ABI call (pinned host in -> H2D -> ENTER -> D2H)
-  roofline : the dominant kernel (k_extend_tile) against the measured HBM peak, using the
-             ALGORITHMIC bytes of the level-streaming model (DESIGN.md / SURVEY.md 8d)
+  roofline : the dominant kernel (k_extend_sym) against the measured HBM peak, using the
+             ALGORITHMIC bytes of the level-streaming model (DESIGN.md / SURVEY.md 8d); the kernel fuses
+             ~10 levels per HBM round trip, so `achieved` exceeds the physical peak and `traffic` (ncu)
+             is ~10x smaller; `integer_pipe` reports the pipe that actually binds it
   cpu_baseline : the CPU oracle (single thread, like the reference library) on a bounded sample
 --impl reference times the CPU restatement of the reference (oracle/, all host threads).
 """
@@ -33,6 +35,21 @@ def modmuls_per_elem(log_n):
     return 2 * log_n * (log_n - 1) + log_n
 
 
+def products_per_elem(log_n):
+    """256-bit field products THIS engine executes per coefficient of ENTER(n) (symmetric butterflies):
+    depth with vectors of length 2^L: pre-scale 1 (L >= 1), 2 L levels of 1/2 product per element, minus the
+    merged centre level (L >= 2), combine 3/2."""
+    tot = 0.0
+    for L in range(log_n):
+        tot += L + (1 if L >= 1 else 0) - (0.5 if L >= 2 else 0) + 1.5
+    return tot
+
+
+# measured on this pool's B200 with tools/microbench.cu (profiles/r01_microbench_pipes.txt)
+IMAD_WIDE_PEAK = 9.1e12      # IMAD.WIDE.U32.X chains /s, the binding pipe of a 256-bit product
+PRODUCT_PEAK = 108e9         # register-resident fp_mul_lazy /s (64 + 13 IMAD.WIDE each)
+
+
 def alg_bytes_per_elem(log_n):
     # level passes 64 B/elem each, matrices ~256 B/elem in total, combines 128 B/elem each (SURVEY.md 8d)
     return 64 * log_n * (log_n - 1) + 256 + 128 * log_n
@@ -45,7 +62,7 @@ def ncu_traffic(log_n):
     try:
         with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
             t = json.load(f)
-        k = t["k_extend_tile"]
+        k = t.get("k_extend_sym") or t["k_extend_tile"]
         return k["dram_total_gb_per_step"], f"GB per step over {k['launches_per_step']} launches (profiles/r01_traffic.json; algorithmic bytes are per step too)"
     except Exception:
         return None, None
@@ -329,7 +346,7 @@ def main():
                 "ms_per_step": e2e_s * 1e3},
         "gpu_launches": int(launches),
         "roofline": {
-            "kernel": "k_extend_tile", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "kernel": "k_extend_sym", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": ncu_traffic(log_n)[0], "traffic_unit": ncu_traffic(log_n)[1],
             "peak_source": peak_src,
             "kernel_ms_per_step": dom["ms_per_step"], "alg_gb_per_step": dom["alg_gb_per_step"],
@@ -337,7 +354,14 @@ def main():
             "whole_step": {"alg_gb": alg_bytes_per_elem(log_n) * n / 1e9,
                            "achieved_gbs": alg_bytes_per_elem(log_n) * n / 1e9 / (ms_per_step * 1e-3),
                            "frac": alg_bytes_per_elem(log_n) * n / 1e9 / (ms_per_step * 1e-3) / peak},
-            "modmul_per_s": modmuls_per_elem(log_n) * n / (ms_per_step * 1e-3),
+            "modmul_per_s_reference_count": modmuls_per_elem(log_n) * n / (ms_per_step * 1e-3),
+            # what actually binds the kernel: the 32x32->64 integer multiplier
+            "integer_pipe": {
+                "products_per_step": products_per_elem(log_n) * n,
+                "products_per_s": products_per_elem(log_n) * n / (ms_per_step * 1e-3),
+                "frac_of_measured_product_peak": products_per_elem(log_n) * n / (ms_per_step * 1e-3) / PRODUCT_PEAK,
+                "peak_source": "tools/microbench.cu on B200: 108 G register-resident 256-bit products/s (IMAD.WIDE.X 9.1 T/s)",
+            },
             "other_kernels": {"k_enter_combine": prof["k_enter_combine"]},
         },
         "clocks": clocks,

@@ -183,6 +183,11 @@ void build_norm_tables(Tree& t, uint32_t k) {
   }
   lv.gx = t.dalloc(hh);
   k::mul_strided(lv.gx, lv.gam[1], lv.xnn_s, 2, 1, hh, st);
+  if (lv.sym && hh >= 2)  // centre constants: level 0 has one twiddle (entry 1) per moiety
+    for (int mu = 0; mu < 2; mu++) {
+      lv.ctr[mu] = t.dalloc(1);
+      k::mul_strided(lv.ctr[mu], lv.tw_r[mu] + 1, lv.tw_d[1 - mu], 1, 1, 1, st);
+    }
 }
 
 // One level of from_tree (src/fftree.rs:318-463): N = 2^k leaves = every (n/N)-th leaf of the top

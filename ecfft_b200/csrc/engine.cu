@@ -80,7 +80,7 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
     static const bool no_fuse = getenv("ECFFT_B200_NO_COMBINE_FUSION") != nullptr;
     if (unscaled && lv.sym && !no_fuse) {  // EXTEND with the combine fused into its last pass
       k::SymCombine c{cur, lv.xnn_s, lv.gam[1], lv.gx, dst};
-      if (k::extend_sym(lv.tw_d[0], lv.tw_r[1], cur, W, ilog2(h), n / h, lv.gami[0], nullptr, &c, st)) {
+      if (k::extend_sym(lv.tw_d[0], lv.tw_r[1], lv.ctr[1], cur, W, ilog2(h), n / h, lv.gami[0], nullptr, &c, st)) {
         cur = dst;
         continue;
       }

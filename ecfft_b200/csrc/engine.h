@@ -72,6 +72,7 @@ struct Level {
   Fp* gam[2] = {nullptr, nullptr};    // h: accumulated scale Gamma^mu_p of the recombine network
   Fp* gami[2] = {nullptr, nullptr};   // h: pre-scale of the decompose network (1/Gamma^mu_p and folded constants)
   Fp* gx = nullptr;                   // h: Gamma^1_i * xnn_s[2i+1] (ENTER combine)
+  Fp* ctr[2] = {nullptr, nullptr};    // sym: 1 element, g_target/g_source at level 0 (index = target moiety)
   bool has_norm() const { return tw_r[0] && tw_r[1] && tw_d[0] && tw_d[1] && gam[0] && gam[1] && gami[0] && gami[1] && gx; }
 };
 
@@ -121,12 +122,12 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
             bool unscaled_out = false);
 void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st);
 // sym_kernel.cu: all passes of the symmetric-butterfly EXTEND (tw_d = 1/g of the source moiety, tw_r = g of
-// the target moiety; pre/post = per-position scales or null).  comb != null fuses ENTER's combine
+// the target moiety, ctr = Level::ctr[target]; pre/post = per-position scales or null).  comb != null fuses ENTER's combine
 // (fftree.rs:155-159) into the last pass: vectors 2w, 2w+1 are u, v of block w, comb->A the depth's
 // unscaled input, and the result goes to comb->out.  Returns false when it does not apply (fewer than 4
 // elements; a depth whose vector length equals the tile cannot take the fused combine).
 struct SymCombine { const Fp* A; const Fp* xnn; const Fp* gam; const Fp* gx; Fp* out; };
-bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
+bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
                 const SymCombine* comb, cudaStream_t st);
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
 void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st);

@@ -29,6 +29,7 @@ struct SymParams {
   Fp* out;
   const Fp* tw_d;   // 1/g of the source moiety, entry 2^j + i
   const Fp* tw_r;   // g of the target moiety
+  const Fp* ctr;    // one element: g_target / g_source at level 0 (the centre of the network)
   const Fp* pre;    // per-position scale applied by the first stage (or null)
   const Fp* post;   // per-position scale applied by the last stage (or null); ignored when comb != 0
   const Fp* A;      // combine epilogue: the unscaled input vectors [u0 | v0] per block
@@ -47,7 +48,7 @@ struct SymParams {
   uint32_t do_d, do_r;
 };
 
-enum : uint32_t { OP_D_HI = 1, OP_D_LO = 2, OP_R_LO = 4, OP_R_HI = 8 };
+enum : uint32_t { OP_D_HI = 1, OP_D_LO = 2, OP_R_LO = 4, OP_R_HI = 8, OP_C_LO = 16 };
 
 struct TileSoA {
   uint4* s;
@@ -74,6 +75,14 @@ __device__ __forceinline__ void sym_r_pair(Fp& a, Fp& b, const Fp& g) {     // y
   Fp t = fp_mul_lazy(g, b);
   b = fp_sub_lazy2_f(a, t);
   a = fp_add_lazy_f(a, t);
+}
+// centre of the network: decompose then recombine at the same level on the same pair is
+// [[1, 1], [1, -1]] diag(1, g_target/g_source) [[1, 1], [1, -1]]: one product with c = g_target/g_source
+__device__ __forceinline__ void sym_c_pair(Fp& a, Fp& b, const Fp& c) {
+  Fp t = fp_mul_lazy(c, fp_sub_lazy2_f(a, b));
+  Fp sum = fp_add_lazy_f(a, b);
+  a = fp_add_lazy_f(sum, t);
+  b = fp_sub_lazy2_f(sum, t);
 }
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
@@ -133,7 +142,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
 
   // ---- stage schedule (see the header comment of quad stages below)
   const uint32_t nlev = p.lvl_hi - p.lvl_lo;
-  const bool mid = p.do_d && p.do_r && nlev >= 2;       // levels lvl_lo+1, lvl_lo run D, D, R, R in one stage
+  const bool mid = p.do_d && p.do_r && nlev >= 2;       // levels lvl_lo+1, lvl_lo run D, D+R (one product), R in one stage
   const uint32_t j_base = p.lvl_lo + (mid ? 2 : 0);     // lowest level of the plain D / R stages
   const uint32_t cnt = p.lvl_hi - j_base, odd = cnt & 1, npairs = cnt >> 1;
   const uint32_t nD = p.do_d ? odd + npairs : 0, nR = p.do_r ? odd + npairs : 0;
@@ -148,13 +157,13 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
       if (odd && sidx == 0) { ops = OP_D_HI; jh = p.lvl_hi - 1; jl = 0; }
       else { const uint32_t u = sidx - odd; ops = OP_D_HI | OP_D_LO; jh = p.lvl_hi - 1 - odd - 2 * u; jl = jh - 1; }
     } else if (mid && sidx == nD) {
-      ops = OP_D_HI | OP_D_LO | OP_R_LO | OP_R_HI; jh = p.lvl_lo + 1; jl = p.lvl_lo;
+      ops = OP_D_HI | OP_C_LO | OP_R_HI; jh = p.lvl_lo + 1; jl = p.lvl_lo;
     } else {
       const uint32_t t = sidx - nD - (mid ? 1 : 0);
       if (t < npairs) { ops = OP_R_LO | OP_R_HI; jl = j_base + 2 * t; jh = jl + 1; }
       else { ops = OP_R_HI; jh = p.lvl_hi - 1; jl = 0; }
     }
-    const bool two = (ops & (OP_D_LO | OP_R_LO)) != 0;
+    const bool two = (ops & (OP_D_LO | OP_R_LO | OP_C_LO)) != 0;
     const uint32_t b_hi = jh + p.boff;
     const uint32_t b_lo = two ? jl + p.boff : (b_hi == 0 ? 1u : b_hi - 1);
     const uint32_t b1 = b_lo < b_hi ? b_lo : b_hi, b2 = b_lo < b_hi ? b_hi : b_lo;
@@ -193,6 +202,11 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
         const Fp gi = fp_load_ro(d_lo + (pa & ml));
         sym_d_pair(x0, x1, gi);
         sym_d_pair(x2, x3, gi);
+      }
+      if (ops & OP_C_LO) {
+        const Fp c_lo = fp_load_ro(p.ctr);
+        sym_c_pair(x0, x1, c_lo);
+        sym_c_pair(x2, x3, c_lo);
       }
       if (ops & OP_R_LO) {
         const Fp g = fp_load_ro(r_lo + (pa & ml));
@@ -296,7 +310,7 @@ static void launch_sym(const SymParams& p, cudaStream_t st) {
 // All passes of the symmetric EXTEND of nvec vectors of length 2^log_h.  comb != null fuses ENTER's combine
 // into the last pass (nvec even: vectors 2w, 2w+1 are u, v of block w); returns false when this depth
 // cannot be fused (the caller then runs EXTEND and the combine kernel separately).
-bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
+bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
                 const SymCombine* comb, cudaStream_t st) {
   const uint32_t LT = sym_log_tile();
   const size_t total = nvec << log_h;
@@ -305,6 +319,7 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* in, Fp* out, uint32_t 
   SymParams p{};
   p.tw_d = tw_d;
   p.tw_r = tw_r;
+  p.ctr = ctr;
   p.total = total;
   p.log_h = log_h;
   if (comb) {

@@ -304,7 +304,7 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
   // symmetric butterflies: the radix-4 register-stage kernel (sym_kernel.cu); the radix-2 tile kernel below
   // remains for the other butterfly forms, for inputs of fewer than 4 elements and ECFFT_B200_SYM_RADIX2
   static const bool radix2 = getenv("ECFFT_B200_SYM_RADIX2") != nullptr;
-  if (norm && lv.sym && !radix2 && extend_sym(lv.tw_d[source], lv.tw_r[target], in, out, log_h, nvec, pre, post, nullptr, st)) return;
+  if (norm && lv.sym && !radix2 && extend_sym(lv.tw_d[source], lv.tw_r[target], lv.ctr[target], in, out, log_h, nvec, pre, post, nullptr, st)) return;
   p.mode = norm ? (lv.sym ? 2 : 1) : 0;
   p.dmat = norm ? lv.tw_d[source] : lv.dmat;
   p.rmat = norm ? lv.tw_r[target] : lv.rmat;
@@ -323,7 +323,7 @@ void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaSt
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
   }
-  if (lv.sym && extend_sym(lv.tw_d[0], lv.tw_r[1], in, out, log_len, 1, nullptr, nullptr, nullptr, st)) return;
+  if (lv.sym && extend_sym(lv.tw_d[0], lv.tw_r[1], lv.ctr[1], in, out, log_len, 1, nullptr, nullptr, nullptr, st)) return;
   TileParams p;
   p.mode = lv.sym ? 2 : 1;
   p.dmat = lv.tw_d[0];

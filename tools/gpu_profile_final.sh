@@ -11,6 +11,6 @@ kill $SMI
 cat gpurun_out/bench_final.json | cut -c1-1500
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_reference.json 2>/dev/null; cat gpurun_out/bench_reference.json | cut -c1-400
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --csv --log-file gpurun_out/launches_final.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline > /dev/null 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_extend_tile -s 64 -c 7 -o gpurun_out/prof_extend_final -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_extend -s 45 -c 6 -o gpurun_out/prof_extend_final -f python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_final.log 2>&1
 python tools/bench_configs.py 22 2>&1 | tee gpurun_out/bench_configs_final.jsonl | cut -c1-150
 ls -la gpurun_out | tail -8

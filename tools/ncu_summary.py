@@ -30,6 +30,8 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     tot, cnt = collections.defaultdict(float), collections.Counter()
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         v = float(row["Metric Value"].replace(",", ""))
         u = row["Metric Unit"]
         v *= {"ns": 1e-6, "nsecond": 1e-6, "us": 1e-3, "usecond": 1e-3, "ms": 1.0, "msecond": 1.0, "s": 1e3, "second": 1e3}.get(u, 1e-6)
