@@ -194,8 +194,9 @@ def main():
     ap.add_argument("--cpu-sample-log-n", type=int, default=18)
     ap.add_argument("--ref-sample-log-n", type=int, default=18)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--multi-gpu", default="sharded", choices=["sharded", "allgather"],
-                    help="top-depth schedule for N>1: fully sharded with pairwise exchanges (default) or one all-gather + replicated top depths")
+    ap.add_argument("--multi-gpu", default="peer", choices=["peer", "sharded", "allgather"],
+                    help="top-depth schedule for N>1: sharded with the kernels reading the partner's buffers over NVLink "
+                         "(peer, default), sharded with NCCL send/recv per straddling level, or one all-gather + replicated top depths")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -211,7 +212,7 @@ def main():
     import torch
     import ecfft_b200
     from ecfft_b200 import _lib
-    from ecfft_b200.dist import enter_sharded, enter_sharded_allgather
+    from ecfft_b200.dist import PeerArena, enter_sharded, enter_sharded_allgather, enter_sharded_peer
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: ecfft_b200 has no CPU fallback")
@@ -241,7 +242,11 @@ def main():
     chunk = n // world
     dev_in = [h[rank * chunk:(rank + 1) * chunk].to(dev) for h in host_in]
 
-    shard_fn = enter_sharded_allgather if args.multi_gpu == "allgather" else enter_sharded
+    if world > 1 and args.multi_gpu == "peer":
+        arena = PeerArena.create(n, local_rank)
+        shard_fn = lambda tree_, x_, n_: enter_sharded_peer(tree_, x_, n_, arena)
+    else:
+        shard_fn = enter_sharded_allgather if args.multi_gpu == "allgather" else enter_sharded
 
     def step(i):
         x = dev_in[i % NBUF]
@@ -338,7 +343,8 @@ def main():
             "workload": f"secp256k1::Fp ENTER n=2^{log_n} (full log^2 recursion) on a 2^{log_n}-leaf FFTree",
             "parallelism": "single GPU" if world == 1 else (
                 f"{world} ranks: local ENTER(n/{world}) + 1 NCCL all-gather + top {world.bit_length() - 1} depths replicated" if args.multi_gpu == "allgather"
-                else f"{world} ranks: local ENTER(n/{world}), top {world.bit_length() - 1} depths sharded (pairwise NCCL send/recv per straddling level), final all-gather of the result"),
+                else f"{world} ranks: local ENTER(n/{world}), top {world.bit_length() - 1} depths sharded (pairwise NCCL send/recv per straddling level), final all-gather of the result" if args.multi_gpu == "sharded"
+                else f"{world} ranks: local ENTER(n/{world}), top {world.bit_length() - 1} depths sharded, straddling butterfly levels and combines read the partner's buffers over NVLink (CUDA-IPC peer memory, flag-ordered), final NCCL all-gather of the result"),
             "inputs": f"{NBUF} rotating coefficient vectors of {n * 32 >> 20} MiB; tables 320 B/leaf resident in HBM; no explicit L2 flush (per-step stream >> 126 MB L2)",
             "tree_build_s": round(t_build, 3),
         },

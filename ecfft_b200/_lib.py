@@ -32,6 +32,8 @@ SYMBOLS = [
     "ecfft_modular_reduce_dev", "ecfft_vanish_dev", "ecfft_enter_range_dev",
     "ecfft_launch_count", "ecfft_profile_enable", "ecfft_profile_read",
     "ecfft_mg_prescale_dev", "ecfft_mg_cross_dev", "ecfft_mg_local_dev", "ecfft_mg_combine_dev",
+    "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free",
+    "ecfft_mg_signal_dev", "ecfft_mg_wait_dev",
 ]
 
 
@@ -94,6 +96,12 @@ def load():
     L.ecfft_mg_cross_dev.argtypes = [vp, sz, ci, ctypes.c_uint, ci, sz, vp, vp, sz, vp, vp]
     L.ecfft_mg_local_dev.argtypes = [vp, sz, vp, sz, vp, vp]
     L.ecfft_mg_combine_dev.argtypes = [vp, sz, sz, vp, vp, vp, vp, sz, vp, vp]
+    L.ecfft_mg_arena_alloc.argtypes = [ci, sz, ctypes.POINTER(vp), ctypes.c_char_p]
+    L.ecfft_mg_arena_open.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
+    L.ecfft_mg_arena_close.argtypes = [vp]
+    L.ecfft_mg_arena_free.argtypes = [vp]
+    L.ecfft_mg_signal_dev.argtypes = [vp, ctypes.c_ulonglong, vp]
+    L.ecfft_mg_wait_dev.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_uint, vp]
     L.ecfft_launch_count.restype = ctypes.c_ulonglong
     L.ecfft_launch_count.argtypes = []
     L.ecfft_profile_enable.restype = None

@@ -455,4 +455,78 @@ int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d
   });
 }
 
+
+// ---- peer-memory arena (include/ecfft_b200.h "peer exchange") ---------------------------------------
+// A flag is one u64 in an arena.  signal: everything enqueued on `stream` before it is visible to every
+// GPU of the node once the flag shows `value` (release at system scope).  wait: the stream does not go on
+// until the flag (usually in a PEER's arena, read over NVLink) is >= value; a wait that is not satisfied
+// within timeout_ms traps, which surfaces as a CUDA error on the next call instead of a hung GPU.
+__global__ void k_mg_signal(unsigned long long* flag, unsigned long long value) {
+  __threadfence_system();
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
+}
+__global__ void k_mg_wait(const unsigned long long* flag, unsigned long long value, unsigned long long timeout_ns) {
+  unsigned long long t0, t, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
+    if (v >= value) break;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    if (t - t0 > timeout_ns) __trap();
+    __nanosleep(200);
+  }
+  __threadfence_system();
+}
+int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* handle64) {
+  return guard([&] {
+    require(d_ptr && handle64 && bytes > 0, ERR_INVALID_ARG, "bad arena arguments");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    ECFFT_CUDA(cudaSetDevice(device));
+    void* p = nullptr;
+    ECFFT_CUDA(cudaMalloc(&p, bytes));
+    ECFFT_CUDA(cudaMemset(p, 0, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+      cudaFree(p);
+      throw Error(ERR_CUDA, std::string("cudaIpcGetMemHandle: ") + cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, 64);
+    *d_ptr = p;
+  });
+}
+int ecfft_mg_arena_open(int device, const unsigned char* handle64, void** d_peer_ptr) {
+  return guard([&] {
+    require(d_peer_ptr && handle64, ERR_INVALID_ARG, "bad arena arguments");
+    ECFFT_CUDA(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    ECFFT_CUDA(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    *d_peer_ptr = p;
+  });
+}
+int ecfft_mg_arena_close(void* d_peer_ptr) {
+  return guard([&] { ECFFT_CUDA(cudaIpcCloseMemHandle(d_peer_ptr)); });
+}
+int ecfft_mg_arena_free(void* d_ptr) {
+  return guard([&] { ECFFT_CUDA(cudaFree(d_ptr)); });
+}
+int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream) {
+  return guard([&] {
+    require(d_flag != nullptr && ((uintptr_t)d_flag & 7) == 0, ERR_INVALID_ARG, "flag pointer must be 8-byte aligned");
+    k_mg_signal<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)d_flag, value);
+    prof::count_launch();
+    ECFFT_CUDA(cudaGetLastError());
+  });
+}
+int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned timeout_ms, void* stream) {
+  return guard([&] {
+    require(d_flag != nullptr && ((uintptr_t)d_flag & 7) == 0, ERR_INVALID_ARG, "flag pointer must be 8-byte aligned");
+    k_mg_wait<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_flag, value, (unsigned long long)timeout_ms * 1000000ull);
+    prof::count_launch();
+    ECFFT_CUDA(cudaGetLastError());
+  });
+}
+
 }  // extern "C"

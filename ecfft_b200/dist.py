@@ -127,3 +127,193 @@ def enter_sharded(tree, chunk, n, group=None, gather=True, comm=None):
     if not gather or world == 1:
         return A
     return comm.all_gather(A)
+
+
+# ----------------------------------------------------------------------------------------------------
+# Peer-memory schedule: the same sharded top depths, but no send/recv — every rank keeps the buffers of
+# the current ENTER in an arena the other ranks of the node map through CUDA IPC, and the butterfly /
+# combine kernels load the partner's operands over NVLink themselves (`ecfft_mg_cross_dev`'s partner
+# pointer and `ecfft_mg_combine_dev`'s u/v pointers are peer pointers).  Ordering is by stream-ordered
+# u64 flags in the arenas (`ecfft_mg_signal_dev` / `ecfft_mg_wait_dev`); every produced buffer of one
+# ENTER has its own slot, so within a call there is nothing to protect against overwriting, and the
+# final all-gather (or barrier) of a call orders it before the next one.
+# ----------------------------------------------------------------------------------------------------
+import ctypes
+
+from . import _lib
+
+_FLAG_BYTES = 4096      # 512 flags: one per synchronisation step of a call
+_WAIT_MS = 20000
+
+
+def _peer_slots(world):
+    """buffers one call produces per rank: A0, then per top depth W_pre, one per cross level, W_local, A_next"""
+    slots, r = 1, 1
+    while r < world:
+        slots += 2 + 2 * (r.bit_length() - 1) + 1
+        r *= 2
+    return slots
+
+
+class PeerArena:
+    """Per-rank arena [flags | slots] plus the peers' mappings.  `PeerArena.create` is collective over the
+    process group; `PeerArena.local_group` builds the arenas of several virtual ranks inside one process
+    (tests: threads on one GPU share plain device pointers)."""
+
+    def __init__(self, rank, world, n, device, own_ptr, bases, owner=True, opened=()):
+        self.rank, self.world, self.n, self.device = rank, world, n, device
+        self.c = n // world
+        self.own = own_ptr
+        self.bases = bases            # bases[r]: rank r's arena as seen from this rank
+        self.epoch = 0
+        self._owner, self._opened = owner, list(opened)
+
+    @staticmethod
+    def nbytes(n, world):
+        return _FLAG_BYTES + _peer_slots(world) * (n // world) * 32
+
+    @classmethod
+    def create(cls, n, device, group=None):
+        L = _lib.load()
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+        _lib.check(L.ecfft_mg_arena_alloc(device, cls.nbytes(n, world), ctypes.byref(own), handle))
+        handles = [None] * world
+        dist.all_gather_object(handles, handle.raw, group=group)
+        bases, opened = [], []
+        for r in range(world):
+            if r == rank:
+                bases.append(own.value)
+                continue
+            p = ctypes.c_void_p()
+            _lib.check(L.ecfft_mg_arena_open(device, handles[r], ctypes.byref(p)))
+            bases.append(p.value)
+            opened.append(p.value)
+        dist.barrier(group=group)
+        return cls(rank, world, n, device, own.value, bases, owner=True, opened=opened)
+
+    @classmethod
+    def local_group(cls, n, world, device):
+        L = _lib.load()
+        ptrs = []
+        for _ in range(world):
+            own, handle = ctypes.c_void_p(), ctypes.create_string_buffer(64)
+            _lib.check(L.ecfft_mg_arena_alloc(device, cls.nbytes(n, world), ctypes.byref(own), handle))
+            ptrs.append(own.value)
+        return [cls(r, world, n, device, ptrs[r], list(ptrs), owner=True) for r in range(world)]
+
+    def slot(self, r, idx, elem_off=0):
+        return self.bases[r] + _FLAG_BYTES + (idx * self.c + elem_off) * 32
+
+    def flag(self, r, sid):
+        return self.bases[r] + 8 * sid
+
+    def close(self):
+        L = _lib.load()
+        for p in self._opened:
+            L.ecfft_mg_arena_close(ctypes.c_void_p(p))
+        self._opened = []
+        if self._owner and self.own:
+            L.ecfft_mg_arena_free(ctypes.c_void_p(self.own))
+            self.own = None
+
+
+def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gather=None, barrier=None):
+    """Fully sharded ENTER with peer-memory exchange.  chunk: this rank's n/G coefficients (CUDA tensor).
+    Returns the full (n, 4) evaluation vector on every rank (gather=True) or this rank's chunk of it.
+    `all_gather` / `barrier` default to the process group's (tests with virtual ranks pass their own)."""
+    L = _lib.load()
+    world, rank = arena.world, arena.rank
+    _check(n, world, chunk)
+    if arena.n != n:
+        raise ValueError("arena was created for a different n")
+    c = n // world
+    log_c = c.bit_length() - 1
+    st = ctypes.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)
+    h = tree._h
+    vp = ctypes.c_void_p
+    arena.epoch += 1
+    epoch = arena.epoch
+    state = {"slot": 0, "sid": 0}
+
+    def new_slot():
+        state["slot"] += 1
+        return state["slot"] - 1
+
+    def sync(peers):
+        """everything this rank has enqueued is published; then wait for the same step of `peers`"""
+        sid = state["sid"]
+        state["sid"] += 1
+        if sid >= _FLAG_BYTES // 8:
+            raise RuntimeError("peer arena: too many synchronisation steps")
+        _lib.check(L.ecfft_mg_signal_dev(vp(arena.flag(rank, sid)), epoch, st))
+        for p in peers:
+            if p != rank:
+                _lib.check(L.ecfft_mg_wait_dev(vp(arena.flag(p, sid)), epoch, _WAIT_MS, st))
+
+    chunk = chunk.contiguous()
+    sA = new_slot()
+    _lib.check(L.ecfft_enter_range_dev(h, vp(chunk.data_ptr()), c, 1, c, vp(arena.slot(rank, sA)), st))
+    out_t = None
+    r, m = 1, 2 * c
+    while m <= n:
+        hlen = m // 2
+        log_h = hlen.bit_length() - 1
+        k = rank % r
+        pos0 = k * c
+        vidx = rank // r
+        block0 = (vidx // 2) * 2 * r
+        # ---- EXTEND -> S1 of the vector this rank holds a chunk of
+        sW = new_slot()
+        _lib.check(L.ecfft_mg_prescale_dev(h, m, pos0, vp(arena.slot(rank, sA)), c, vp(arena.slot(rank, sW)), st))
+        for phase, levels in ((0, range(log_h - 1, log_c - 1, -1)), (None, None), (1, range(log_c, log_h))):
+            if phase is None:                                   # all levels with half-stride < c: rank-local
+                sN = new_slot()
+                _lib.check(L.ecfft_mg_local_dev(h, m, vp(arena.slot(rank, sW)), c, vp(arena.slot(rank, sN)), st))
+                sW = sN
+                continue
+            for j in levels:                                    # levels whose pairs straddle two ranks
+                bit = (k >> (j - log_c)) & 1
+                peer = rank ^ (1 << (j - log_c))
+                sync([peer])
+                sN = new_slot()
+                _lib.check(L.ecfft_mg_cross_dev(h, m, phase, j, bit, pos0 - (bit << j), vp(arena.slot(rank, sW)),
+                                                vp(arena.slot(peer, sW)), c, vp(arena.slot(rank, sN)), st))
+                sW = sN
+        # ---- combine (src/fftree.rs:155-159): output rank kp of the block takes i in [kp c/2, (kp+1) c/2)
+        # straight out of the u-rank's and the v-rank's A and W
+        half = c // 2
+        kp = rank - block0
+        usrc, vsrc = block0 + kp // 2, block0 + r + kp // 2
+        off = (kp % 2) * half
+        sync([usrc, vsrc])
+        last = 2 * m > n
+        if last and not gather:
+            out_t = torch.empty((c, 4), dtype=chunk.dtype, device=chunk.device)
+            dst = out_t.data_ptr()
+            sNext = None
+        elif last:
+            out_t = torch.empty((c, 4), dtype=chunk.dtype, device=chunk.device)
+            dst = out_t.data_ptr()
+            sNext = None
+        else:
+            sNext = new_slot()
+            dst = arena.slot(rank, sNext)
+        _lib.check(L.ecfft_mg_combine_dev(h, m, kp * half, vp(arena.slot(usrc, sA, off)), vp(arena.slot(vsrc, sA, off)),
+                                          vp(arena.slot(usrc, sW, off)), vp(arena.slot(vsrc, sW, off)), half, vp(dst), st))
+        sA = sNext
+        r *= 2
+        m *= 2
+    if out_t is None:                                           # world == 1
+        out_t = torch.empty((c, 4), dtype=chunk.dtype, device=chunk.device)
+        _lib.check(L.ecfft_enter_range_dev(h, vp(arena.slot(rank, 0)), c, c, c, vp(out_t.data_ptr()), st))
+    if gather and world > 1:
+        if all_gather is not None:
+            return all_gather(out_t)
+        full = torch.empty((n, 4), dtype=chunk.dtype, device=chunk.device)
+        dist.all_gather_into_tensor(full, out_t, group=group)
+        return full
+    # the peers may still be reading this rank's slots: order the call before the next one
+    if world > 1:
+        (barrier or (lambda: dist.barrier(group=group)))()
+    return out_t

@@ -123,6 +123,20 @@ int ecfft_mg_local_dev(const ecfft_tree* t, size_t m, const void* d_in, size_t c
 int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d_u0, const void* d_v0, const void* d_u1,
                          const void* d_v1, size_t count, void* d_out, void* stream);
 
+/* Peer exchange: instead of a send/recv per straddling level, `d_partner` of
+ * ecfft_mg_cross_dev and the u/v pointers of ecfft_mg_combine_dev may point into ANOTHER GPU's memory,
+ * mapped through CUDA IPC — the butterfly kernel then loads the partner's operands over NVLink itself.
+ *   arena_alloc : zeroed device memory on `device` plus its 64-byte IPC handle (to be sent to the peers)
+ *   arena_open  : map a peer's arena into this process (peer access enabled lazily); arena_close unmaps
+ *   signal/wait : stream-ordered u64 flags inside arenas (release / acquire at system scope).  A wait not
+ *                 satisfied within timeout_ms traps (a CUDA error on the next call, never a hung GPU). */
+int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* handle64);
+int ecfft_mg_arena_open(int device, const unsigned char* handle64, void** d_peer_ptr);
+int ecfft_mg_arena_close(void* d_peer_ptr);
+int ecfft_mg_arena_free(void* d_ptr);
+int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream);
+int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned timeout_ms, void* stream);
+
 /* ---- instrumentation used by bench.py ------------------------------------------------- */
 /* kernels launched by this library since it was loaded */
 unsigned long long ecfft_launch_count(void);

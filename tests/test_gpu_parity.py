@@ -376,3 +376,64 @@ def test_sharded_schedule_with_virtual_ranks(trees, oracle_mod, world):
         eq(full, want)
         eq(ag, want)
         eq(part, want[rank * c:(rank + 1) * c])
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_peer_memory_schedule_with_virtual_ranks(trees, oracle_mod, world):
+    """ecfft_b200.dist.enter_sharded_peer — butterfly / combine kernels reading the partner's buffers
+    through arena pointers, ordered by ecfft_mg_signal_dev / ecfft_mg_wait_dev flags — with `world` virtual
+    ranks (threads, one CUDA stream each) whose arenas live on ONE GPU.  Two calls per rank exercise the
+    epoch counter and slot reuse.  (Across GPUs the same pointers are CUDA-IPC mappings; bench.py --gpus N.)"""
+    import threading
+    import torch
+    from ecfft_b200.dist import PeerArena, enter_sharded_peer
+    gpu, cpu = trees
+    n = 1 << 14
+    x = oracle_mod.random_elements(n, seed=40 + world)
+    want = cpu.enter(x)
+    xd = torch.from_numpy(x.view(np.int64)).cuda()
+    c = n // world
+    arenas = PeerArena.local_group(n, world, device=0)
+    slots, barrier = [None] * world, threading.Barrier(world)
+    results, errors = [None] * world, []
+    torch.cuda.synchronize()
+
+    def run(rank):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                def all_gather(t):
+                    stream.synchronize()
+                    slots[rank] = t
+                    barrier.wait()
+                    out = torch.cat([slots[r] for r in range(world)])
+                    stream.synchronize()
+                    barrier.wait()
+                    return out
+
+                def bar():
+                    stream.synchronize()
+                    barrier.wait()
+
+                chunk = xd[rank * c:(rank + 1) * c]
+                enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar)
+                full = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar)
+                part = enter_sharded_peer(gpu, chunk, n, arenas[rank], gather=False, all_gather=all_gather, barrier=bar)
+                stream.synchronize()
+                results[rank] = (full.cpu().numpy().view(np.uint64), part.cpu().numpy().view(np.uint64))
+        except Exception as e:  # surface failures instead of deadlocking the other ranks
+            errors.append(repr(e))
+            barrier.abort()
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    for rank in range(world):
+        full, part = results[rank]
+        eq(full, want)
+        eq(part, want[rank * c:(rank + 1) * c])
+    for a in arenas:
+        a.close()
