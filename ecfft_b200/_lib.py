@@ -33,7 +33,7 @@ SYMBOLS = [
     "ecfft_launch_count", "ecfft_profile_enable", "ecfft_profile_read",
     "ecfft_mg_prescale_dev", "ecfft_mg_cross_dev", "ecfft_mg_local_dev", "ecfft_mg_combine_dev",
     "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free",
-    "ecfft_mg_signal_dev", "ecfft_mg_wait_dev",
+    "ecfft_mg_signal_dev", "ecfft_mg_wait_dev", "ecfft_mg_arena_bytes", "ecfft_enter_peer_dev",
 ]
 
 
@@ -100,6 +100,8 @@ def load():
     L.ecfft_mg_arena_open.argtypes = [ci, ctypes.c_char_p, ctypes.POINTER(vp)]
     L.ecfft_mg_arena_close.argtypes = [vp]
     L.ecfft_mg_arena_free.argtypes = [vp]
+    L.ecfft_mg_arena_bytes.argtypes = [sz, ci, psz]
+    L.ecfft_enter_peer_dev.argtypes = [vp, vp, sz, ci, ci, pvp, ctypes.c_ulonglong, vp, vp]
     L.ecfft_mg_signal_dev.argtypes = [vp, ctypes.c_ulonglong, vp]
     L.ecfft_mg_wait_dev.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_uint, vp]
     L.ecfft_launch_count.restype = ctypes.c_ulonglong

@@ -461,22 +461,6 @@ int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d
 // GPU of the node once the flag shows `value` (release at system scope).  wait: the stream does not go on
 // until the flag (usually in a PEER's arena, read over NVLink) is >= value; a wait that is not satisfied
 // within timeout_ms traps, which surfaces as a CUDA error on the next call instead of a hung GPU.
-__global__ void k_mg_signal(unsigned long long* flag, unsigned long long value) {
-  __threadfence_system();
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(value) : "memory");
-}
-__global__ void k_mg_wait(const unsigned long long* flag, unsigned long long value, unsigned long long timeout_ns) {
-  unsigned long long t0, t, v;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flag) : "memory");
-    if (v >= value) break;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    if (t - t0 > timeout_ns) __trap();
-    __nanosleep(200);
-  }
-  __threadfence_system();
-}
 int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* handle64) {
   return guard([&] {
     require(d_ptr && handle64 && bytes > 0, ERR_INVALID_ARG, "bad arena arguments");
@@ -512,20 +496,30 @@ int ecfft_mg_arena_close(void* d_peer_ptr) {
 int ecfft_mg_arena_free(void* d_ptr) {
   return guard([&] { ECFFT_CUDA(cudaFree(d_ptr)); });
 }
+int ecfft_mg_arena_bytes(size_t n, int world, size_t* bytes) {
+  return guard([&] {
+    require(bytes != nullptr, ERR_INVALID_ARG, "null output");
+    *bytes = peer_arena_bytes(n, world);
+  });
+}
+int ecfft_enter_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
+                         unsigned long long epoch, void* d_out_chunk, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    require(arena_bases != nullptr, ERR_INVALID_ARG, "null arena table");
+    enter_peer(eng, dptr(d_chunk), n, rank, world, arena_bases, epoch, dptr(d_out_chunk));
+  });
+}
 int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream) {
   return guard([&] {
     require(d_flag != nullptr && ((uintptr_t)d_flag & 7) == 0, ERR_INVALID_ARG, "flag pointer must be 8-byte aligned");
-    k_mg_signal<<<1, 1, 0, (cudaStream_t)stream>>>((unsigned long long*)d_flag, value);
-    prof::count_launch();
-    ECFFT_CUDA(cudaGetLastError());
+    k::mg_sync((unsigned long long*)d_flag, value, nullptr, nullptr, 0, (cudaStream_t)stream);
   });
 }
 int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned timeout_ms, void* stream) {
   return guard([&] {
     require(d_flag != nullptr && ((uintptr_t)d_flag & 7) == 0, ERR_INVALID_ARG, "flag pointer must be 8-byte aligned");
-    k_mg_wait<<<1, 1, 0, (cudaStream_t)stream>>>((const unsigned long long*)d_flag, value, (unsigned long long)timeout_ms * 1000000ull);
-    prof::count_launch();
-    ECFFT_CUDA(cudaGetLastError());
+    k::mg_sync(nullptr, value, (const unsigned long long*)d_flag, nullptr, timeout_ms, (cudaStream_t)stream);
   });
 }
 

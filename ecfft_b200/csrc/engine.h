@@ -120,7 +120,7 @@ namespace k {
 // the final Gamma scaling to the caller (ENTER folds it into its combine).
 void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st,
             bool unscaled_out = false);
-void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st);
+void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st, const Fp* pre = nullptr);
 // sym_kernel.cu: all passes of the symmetric-butterfly EXTEND (tw_d = 1/g of the source moiety, tw_r = g of
 // the target moiety, ctr = Level::ctr[target]; pre/post = per-position scales or null).  comb != null fuses ENTER's combine
 // (fftree.rs:155-159) into the last pass: vectors 2w, 2w+1 are u, v of block w, comb->A the depth's
@@ -130,6 +130,8 @@ struct SymCombine { const Fp* A; const Fp* xnn; const Fp* gam; const Fp* gx; Fp*
 bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
                 const SymCombine* comb, cudaStream_t st);
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
+void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
+             const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st);
 void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st);
 int butterfly_mode();  // ECFFT_B200_BUTTERFLY: 2 = symmetric (default), 1 = normalised, 0 = 2x2 matrices
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
@@ -201,6 +203,15 @@ struct Engine {
   void mod_user(const Fp* evals, const Fp* a_mont, const Fp* c_mont, size_t n, Fp* out) const;
   void vanish(const Fp* domain, Fp* out, size_t n, DataForm form) const;
 };
+
+// ---- sharded.cu: the per-rank schedule of the multi-GPU ENTER over peer-mapped arenas ----
+// Arena of a rank: [ECFFT_MG_FLAG_BYTES of u64 flags | slots of n/world elements]; bases[r] is rank r's
+// arena as mapped into this process.  Writes this rank's n/world evaluations (positions
+// [rank n/world, (rank+1) n/world)) to out_chunk.
+static constexpr size_t MG_FLAG_BYTES = 4096;
+size_t peer_arena_bytes(size_t n, int world);
+void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int world, void* const* bases,
+                unsigned long long epoch, Fp* out_chunk);
 
 // ---- builder.cu / serialize.cu --------------------------------------------------------------
 Tree* build_secp256k1(size_t n, int parts, int device);                                     // lib.rs:39-85

@@ -419,6 +419,38 @@ void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, c
     fp_store(out + e, fp_canon(res));
   });
 }
+// Stream-ordered flags in peer-mapped arenas (include/ecfft_b200.h "peer exchange").  One thread: publish
+// `value` in own_flag (release at system scope: everything enqueued before is visible to the node), then
+// spin until each given peer flag shows >= value.  A wait not satisfied within the timeout traps — a CUDA
+// error on the next call instead of a hung GPU.
+__global__ void k_mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
+                          const unsigned long long* wait_b, unsigned long long timeout_ns) {
+  if (own_flag) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(own_flag), "l"(value) : "memory");
+  }
+  const unsigned long long* w[2] = {wait_a, wait_b};
+  unsigned long long t0, t, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int i = 0; i < 2; i++) {
+    if (!w[i]) continue;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w[i]) : "memory");
+      if (v >= value) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) __trap();
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+}
+void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
+             const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st) {
+  k_mg_sync<<<1, 1, 0, st>>>(own_flag, value, wait_a, wait_b, (unsigned long long)timeout_ms * 1000000ull);
+  prof::count_launch();
+  ECFFT_CUDA(cudaGetLastError());
+}
+
 // out[2t] = u0[t] + v0[t]*xnn[2(i0+t)], out[2t+1] = gam1[i0+t]*u1[t] + gx[i0+t]*v1[t]  (u1, v1 unscaled)
 void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st) {
   if (!lv.gx || !lv.gam[1]) throw Error(ERR_MISSING_TABLES, "mg_combine: normalised tables missing");

@@ -53,6 +53,8 @@ class TorchComm:
 def _check(n, world, chunk):
     if n % world or (n // world) & (n // world - 1) or world & (world - 1):
         raise ValueError("world_size and n / world_size must be powers of two")
+    if world > 1 and n // world < 2:
+        raise ValueError("the sharded schedules need at least 2 coefficients per rank")
     if chunk.shape[0] != n // world:
         raise ValueError("chunk must hold n / world_size coefficients")
 
@@ -170,7 +172,9 @@ class PeerArena:
 
     @staticmethod
     def nbytes(n, world):
-        return _FLAG_BYTES + _peer_slots(world) * (n // world) * 32
+        size = ctypes.c_size_t()
+        _lib.check(_lib.load().ecfft_mg_arena_bytes(n, world, ctypes.byref(size)))   # what ecfft_enter_peer_dev needs
+        return max(size.value, _FLAG_BYTES + _peer_slots(world) * (n // world) * 32)
 
     @classmethod
     def create(cls, n, device, group=None):
@@ -218,15 +222,39 @@ class PeerArena:
             self.own = None
 
 
-def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gather=None, barrier=None):
+def _finish_peer(out_t, n, world, group, gather, all_gather, barrier):
+    if gather and world > 1:
+        if all_gather is not None:
+            return all_gather(out_t)
+        full = torch.empty((n, 4), dtype=out_t.dtype, device=out_t.device)
+        dist.all_gather_into_tensor(full, out_t, group=group)
+        return full
+    # the peers may still be reading this rank's slots: order the call before the next one
+    if world > 1:
+        (barrier or (lambda: dist.barrier(group=group)))()
+    return out_t
+
+
+def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gather=None, barrier=None, native=True):
     """Fully sharded ENTER with peer-memory exchange.  chunk: this rank's n/G coefficients (CUDA tensor).
     Returns the full (n, 4) evaluation vector on every rank (gather=True) or this rank's chunk of it.
-    `all_gather` / `barrier` default to the process group's (tests with virtual ranks pass their own)."""
+    `all_gather` / `barrier` default to the process group's (tests with virtual ranks pass their own).
+    native=True runs the whole per-rank schedule inside the library (`ecfft_enter_peer_dev`,
+    csrc/sharded.cu); native=False drives the same building blocks step by step from here."""
     L = _lib.load()
     world, rank = arena.world, arena.rank
     _check(n, world, chunk)
     if arena.n != n:
         raise ValueError("arena was created for a different n")
+    if native:
+        chunk = chunk.contiguous()
+        arena.epoch += 1
+        out_t = torch.empty((n // world, 4), dtype=chunk.dtype, device=chunk.device)
+        bases = (ctypes.c_void_p * world)(*arena.bases)
+        _lib.check(L.ecfft_enter_peer_dev(tree._h, ctypes.c_void_p(chunk.data_ptr()), n, rank, world, bases, arena.epoch,
+                                          ctypes.c_void_p(out_t.data_ptr()),
+                                          ctypes.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)))
+        return _finish_peer(out_t, n, world, group, gather, all_gather, barrier)
     c = n // world
     log_c = c.bit_length() - 1
     st = ctypes.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)
@@ -307,13 +335,4 @@ def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gathe
     if out_t is None:                                           # world == 1
         out_t = torch.empty((c, 4), dtype=chunk.dtype, device=chunk.device)
         _lib.check(L.ecfft_enter_range_dev(h, vp(arena.slot(rank, 0)), c, c, c, vp(out_t.data_ptr()), st))
-    if gather and world > 1:
-        if all_gather is not None:
-            return all_gather(out_t)
-        full = torch.empty((n, 4), dtype=chunk.dtype, device=chunk.device)
-        dist.all_gather_into_tensor(full, out_t, group=group)
-        return full
-    # the peers may still be reading this rank's slots: order the call before the next one
-    if world > 1:
-        (barrier or (lambda: dist.barrier(group=group)))()
-    return out_t
+    return _finish_peer(out_t, n, world, group, gather, all_gather, barrier)

@@ -130,12 +130,21 @@ int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d
  *   arena_open  : map a peer's arena into this process (peer access enabled lazily); arena_close unmaps
  *   signal/wait : stream-ordered u64 flags inside arenas (release / acquire at system scope).  A wait not
  *                 satisfied within timeout_ms traps (a CUDA error on the next call, never a hung GPU). */
+int ecfft_mg_arena_bytes(size_t n, int world, size_t* bytes);   /* arena size ecfft_enter_peer_dev needs */
 int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* handle64);
 int ecfft_mg_arena_open(int device, const unsigned char* handle64, void** d_peer_ptr);
 int ecfft_mg_arena_close(void* d_peer_ptr);
 int ecfft_mg_arena_free(void* d_ptr);
 int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream);
 int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned timeout_ms, void* stream);
+/* The whole per-rank schedule of the sharded ENTER in one call (reference src/fftree.rs:143-161 for the
+ * coefficient chunk of `rank`, then the top log2(world) depths over peer memory): d_chunk holds this
+ * rank's n/world coefficients, arena_bases[r] is rank r's arena as mapped into this process
+ * (arena_bases[rank] = this rank's own), epoch must grow by one per call on all ranks alike;
+ * d_out_chunk receives evaluations [rank n/world, (rank+1) n/world).  Before the next call the ranks must
+ * have passed a barrier or collective (the peers may still be reading this rank's arena). */
+int ecfft_enter_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
+                         unsigned long long epoch, void* d_out_chunk, void* stream);
 
 /* ---- instrumentation used by bench.py ------------------------------------------------- */
 /* kernels launched by this library since it was loaded */

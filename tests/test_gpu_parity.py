@@ -383,7 +383,8 @@ def test_peer_memory_schedule_with_virtual_ranks(trees, oracle_mod, world):
     """ecfft_b200.dist.enter_sharded_peer — butterfly / combine kernels reading the partner's buffers
     through arena pointers, ordered by ecfft_mg_signal_dev / ecfft_mg_wait_dev flags — with `world` virtual
     ranks (threads, one CUDA stream each) whose arenas live on ONE GPU.  Two calls per rank exercise the
-    epoch counter and slot reuse.  (Across GPUs the same pointers are CUDA-IPC mappings; bench.py --gpus N.)"""
+    epoch counter and slot reuse; both the in-library schedule (ecfft_enter_peer_dev) and the step-by-step
+    one run.  (Across GPUs the same pointers are CUDA-IPC mappings; bench.py --gpus N.)"""
     import threading
     import torch
     from ecfft_b200.dist import PeerArena, enter_sharded_peer
@@ -419,8 +420,10 @@ def test_peer_memory_schedule_with_virtual_ranks(trees, oracle_mod, world):
                 enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar)
                 full = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar)
                 part = enter_sharded_peer(gpu, chunk, n, arenas[rank], gather=False, all_gather=all_gather, barrier=bar)
+                step = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar, native=False)
                 stream.synchronize()
-                results[rank] = (full.cpu().numpy().view(np.uint64), part.cpu().numpy().view(np.uint64))
+                results[rank] = (full.cpu().numpy().view(np.uint64), part.cpu().numpy().view(np.uint64),
+                                 step.cpu().numpy().view(np.uint64))
         except Exception as e:  # surface failures instead of deadlocking the other ranks
             errors.append(repr(e))
             barrier.abort()
@@ -432,8 +435,9 @@ def test_peer_memory_schedule_with_virtual_ranks(trees, oracle_mod, world):
         t.join(timeout=300)
     assert not errors, errors
     for rank in range(world):
-        full, part = results[rank]
+        full, part, step = results[rank]
         eq(full, want)
+        eq(step, want)
         eq(part, want[rank * c:(rank + 1) * c])
     for a in arenas:
         a.close()

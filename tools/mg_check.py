@@ -31,6 +31,7 @@ def main():
     for rep in range(3):
         got = enter_sharded_peer(tree, chunk, n, arena)
         ok = ok and bool((got == want).all())
+    ok = ok and bool((enter_sharded_peer(tree, chunk, n, arena, native=False) == want).all())   # step-by-step driver
     part = enter_sharded_peer(tree, chunk, n, arena, gather=False)
     ok = ok and bool((part == want[rank * c:(rank + 1) * c]).all())
     ok_nccl = bool((enter_sharded(tree, chunk, n) == want).all()) and bool((enter_sharded_allgather(tree, chunk, n) == want).all())
