@@ -97,13 +97,15 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
 
 // FFTree::redc_impl, src/fftree.rs:232-259, for nvec vectors of length len sharing `a`
 // (plain form).  a0inv (= 1/a[2i], plain) may be supplied when already known.
-void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out) const {
+void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out,
+                  const Fp* c_or_null) const {
   const Level& lv = level_for(len);
   if (len < 2) throw Error(ERR_INVALID_ARG, "redc: length must be >= 2");
   const Fp* zinv = moiety == S0 ? lv.z0_inv_s1 : lv.z1_inv_s0;
   if (!zinv) throw Error(ERR_MISSING_TABLES, "redc: tree was built without the Z tables");
   const size_t h = len / 2;
   const uint32_t log_h = ilog2(h);
+  const Moiety other = moiety == S1 ? S0 : S1;
   Fp* a0inv_own = nullptr;
   if (!a0inv_or_null) {
     a0inv_own = tmp(h);
@@ -111,17 +113,45 @@ void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, s
     k::batch_inverse(a0inv_own, h, st);
     a0inv_or_null = a0inv_own;
   }
+  static const bool no_fuse = getenv("ECFFT_B200_NO_REDC_FUSION") != nullptr;
+  if (lv.sym && lv.has_norm() && k::butterfly_mode() != 0 && !no_fuse && log_h >= 1 && (nvec << log_h) >= 4) {
+    // Fused form: the de-interleave, the two pointwise steps and the interleave ride the two EXTENDs as
+    // stride-2 views and per-position tables (k_extend_sym): no pointwise pass over the data.
+    //   EXTEND 1: reads evals[2i], pre-scale a0inv*gami (*c), stores out[2i+1] = evals[2i+1]*zinv(*c) - g1^*(gam*a*zinv)
+    //   EXTEND 2: reads out[2i+1] (= h1), stores out[2i] = h0
+    Fp* tabs = tmp(3 * h);
+    Fp* work = tmp(h * nvec);
+    Fp *P1 = tabs, *Kp = tabs + h, *Zc = tabs + 2 * h;
+    k::redc_tables(P1, Kp, Zc, a_plain, a0inv_or_null, zinv, lv.gami[moiety], lv.gam[other], c_or_null, h, st);
+    k::SymIO io1{1, 0, 1, 1, evals, 1, 1, Zc, work};
+    k::SymIO io2{1, 1, 1, 0, nullptr, 0, 0, nullptr, work};
+    const bool ok1 = k::extend_sym(lv.tw_d[moiety], lv.tw_r[other], lv.ctr[other], evals, out, log_h, nvec, P1, Kp, nullptr, st, &io1);
+    const bool ok2 = ok1 && k::extend_sym(lv.tw_d[other], lv.tw_r[moiety], lv.ctr[moiety], out, out, log_h, nvec, lv.gami[other], lv.gam[moiety], nullptr, st, &io2);
+    release(tabs);
+    release(work);
+    release(a0inv_own);
+    if (!ok2) throw Error(ERR_INVALID_ARG, "redc: fused EXTEND refused an input it should take");
+    return;
+  }
+  const Fp* src = evals;
+  Fp* scaled = nullptr;
+  if (c_or_null) {
+    scaled = tmp(len * nvec);
+    k::mul_bcast(scaled, evals, c_or_null, len, nvec, st);
+    src = scaled;
+  }
   Fp* t0 = tmp(h * nvec);
   Fp* g1 = tmp(h * nvec);
-  k::redc_pre(t0, evals, a0inv_or_null, h, nvec, st);
-  k::extend(lv, t0, g1, log_h, nvec, moiety == S1 ? S0 : S1, st);
+  k::redc_pre(t0, src, a0inv_or_null, h, nvec, st);
+  k::extend(lv, t0, g1, log_h, nvec, other, st);
   Fp* h1 = t0;  // t0 is dead once g1 exists
-  k::redc_mid(h1, evals, g1, a_plain, zinv, h, nvec, st);
+  k::redc_mid(h1, src, g1, a_plain, zinv, h, nvec, st);
   Fp* h0 = g1;
   k::extend(lv, h1, h0, log_h, nvec, moiety, st);
   k::interleave(out, h0, h1, h * nvec, st);
   release(t0);
   release(g1);
+  release(scaled);
   release(a0inv_own);
 }
 
@@ -137,8 +167,7 @@ void Engine::modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_
   }
   Fp* hb = tmp(len * nvec);
   redc(evals, a_plain, a0inv_or_null, len, nvec, S0, hb);
-  k::mul_bcast(hb, hb, c_plain, len, nvec, st);
-  redc(hb, a_plain, a0inv_or_null, len, nvec, S0, out);
+  redc(hb, a_plain, a0inv_or_null, len, nvec, S0, out, c_plain);  // the multiplication by c rides the second REDC
   release(hb);
   release(a0inv_own);
 }

@@ -127,8 +127,12 @@ void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaSt
 // unscaled input, and the result goes to comb->out.  Returns false when it does not apply (fewer than 4
 // elements; a depth whose vector length equals the tile cannot take the fused combine).
 struct SymCombine { const Fp* A; const Fp* xnn; const Fp* gam; const Fp* gx; Fp* out; };
+// Strided views for REDC (fftree.rs:232-259): logical element g is read at in[(g << in_shift) + in_off] and
+// written at out[(g << out_shift) + out_off]; with E the store is E[(g << e_shift) + e_off] * Z[i] + x * post[i]
+// (i = position within the vector).  work: contiguous scratch of nvec * h elements for multi-pass EXTENDs.
+struct SymIO { uint32_t in_shift, in_off, out_shift, out_off; const Fp* E; uint32_t e_shift, e_off; const Fp* Z; Fp* work; };
 bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
-                const SymCombine* comb, cudaStream_t st);
+                const SymCombine* comb, cudaStream_t st, const SymIO* io = nullptr);
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
 void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
              const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st);
@@ -147,6 +151,8 @@ void copy_strided(Fp* out, const Fp* in, size_t count, size_t in_stride, cudaStr
 // REDC pieces (fftree.rs:232-259), vectors of length 2h, a/zinv shared by all vectors
 void redc_pre(Fp* t0, const Fp* evals, const Fp* a0inv, size_t h, size_t nvec, cudaStream_t st);
 void redc_mid(Fp* h1, const Fp* evals, const Fp* g1, const Fp* a, const Fp* zinv, size_t h, size_t nvec, cudaStream_t st);
+void redc_tables(Fp* P1, Fp* Kp, Fp* Zc, const Fp* a, const Fp* a0inv, const Fp* zinv, const Fp* gami_src, const Fp* gam_tgt,
+                 const Fp* c, size_t h, cudaStream_t st);
 // EXIT split (fftree.rs:206-220): next[v] = [ M[v][::2] | (e[v][::2]-M[v][::2]) * xnn_inv[::2] ]
 void exit_split(Fp* next, const Fp* evals, const Fp* M, const Fp* xnn_inv, size_t h, size_t nvec, cudaStream_t st);
 // VANISH pieces (fftree.rs:291-308)
@@ -190,7 +196,9 @@ struct Engine {
 
   // batched primitives: nvec contiguous vectors
   void extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target) const;
-  void redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out) const;
+  // c_or_null: evals are to be multiplied pointwise by c first (MOD's middle step, folded into the tables)
+  void redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out,
+            const Fp* c_or_null = nullptr) const;
   void modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, const Fp* c_plain, size_t len, size_t nvec, Fp* out) const;
 
   // the FFTree<F> surface (fftree.rs:72-316) on device buffers

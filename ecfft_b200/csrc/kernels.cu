@@ -180,6 +180,23 @@ void redc_mid(Fp* h1, const Fp* evals, const Fp* g1, const Fp* a, const Fp* zinv
     fp_store(h1 + idx, fp_mul(d, fp_load_ro(zinv + i)));
   });
 }
+// Tables of the fused REDC (engine.cu): P1 = a0inv * gami_src (* c_even), Kp = -(gam_tgt * a_odd * zinv),
+// Zc = zinv (* c_odd); c (MOD's multiplier, fftree.rs:279) may be null.
+void redc_tables(Fp* P1, Fp* Kp, Fp* Zc, const Fp* a, const Fp* a0inv, const Fp* zinv, const Fp* gami_src, const Fp* gam_tgt,
+                 const Fp* c, size_t h, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t i) {
+    Fp p1 = fp_mul(fp_load(a0inv + i), fp_load_ro(gami_src + i));
+    Fp zc = fp_load(zinv + i);
+    Fp kp = fp_mul(fp_mul(fp_load_ro(gam_tgt + i), fp_load(a + 2 * i + 1)), zc);
+    if (c) {
+      p1 = fp_mul(p1, fp_load(c + 2 * i));
+      zc = fp_mul(zc, fp_load(c + 2 * i + 1));
+    }
+    fp_store(P1 + i, p1);
+    fp_store(Kp + i, fp_neg(kp));
+    fp_store(Zc + i, zc);
+  });
+}
 void exit_split(Fp* next, const Fp* evals, const Fp* M, const Fp* xnn_inv, size_t h, size_t nvec, cudaStream_t st) {
   map(h * nvec, st, [=] __device__(size_t idx) {
     size_t v = idx / h, i = idx % h;

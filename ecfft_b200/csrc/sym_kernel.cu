@@ -13,10 +13,12 @@
 // A thread takes FOUR elements into registers and runs two levels on them (four at the centre of the
 // inner pass: decompose 1, 0 then recombine 0, 1) per shared-memory round trip.  The tile arrives by
 // cp.async (no registers held across the HBM latency); the pre-scale is applied by the first stage as
-// it reads the tile, the post-scale and the canonical reduction by the last stage, which stores to
-// global memory directly — or, in ENTER, leaves the extended values in shared memory for the combine
-// epilogue  out[2i] = u0[i] + v0[i] xnn[2i],  out[2i+1] = gam[i] u1[i] + gx[i] v1[i],
-// for which a tile holds the same positions of the two sibling vectors u and v.
+// it reads the tile; after the last stage an epilogue reads the tile back in natural order and either
+// stores it (post-scale, canonical reduction, coalesced) or, in ENTER, performs the combine
+//   out[2i] = u0[i] + v0[i] xnn[2i],  out[2i+1] = gam[i] u1[i] + gx[i] v1[i],
+// for which a tile holds the same positions of the two sibling vectors u and v.  The first load and the
+// last store can be stride-2 views and the store can add a second operand (e1 * Z + x * post), which is
+// how REDC's de-interleave, pointwise steps and interleave (src/fftree.rs:232-259) ride the two EXTENDs.
 #include <cstdlib>
 
 #include "engine.h"
@@ -46,6 +48,12 @@ struct SymParams {
   uint32_t pair;              // strided: top tile bit selects vector 2w / 2w+1
   uint32_t comb;              // 1: combine epilogue
   uint32_t do_d, do_r;
+  // strided views (REDC's de-interleave / interleave, src/fftree.rs:234, 258): logical element g of the
+  // batch is read at in[(g << in_shift) + in_off] by the first pass and written at out[(g << out_shift) +
+  // out_off] by the last; E/Z: the last pass stores E[(g << e_shift) + e_off] * Z[i] + x * post[i]
+  uint32_t in_shift, in_off, out_shift, out_off, e_shift, e_off;
+  const Fp* E;
+  const Fp* Z;
 };
 
 enum : uint32_t { OP_D_HI = 1, OP_D_LO = 2, OP_R_LO = 4, OP_R_HI = 8, OP_C_LO = 16 };
@@ -129,7 +137,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
     tm.map(e, goff, pos);
     const unsigned long long g = gbase + goff;
     if (g < p.total) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.in + g);
+      const uint4* src = reinterpret_cast<const uint4*>(p.in + ((g << p.in_shift) + p.in_off));
       cp_async16(&s.s[e], src);
       cp_async16(&s.s[T + e], src + 1);
     } else {
@@ -170,8 +178,6 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
     const uint32_t S_lo = 1u << b_lo, S_hi = 1u << b_hi;
     const uint32_t mh = (1u << jh) - 1, ml = (1u << jl) - 1;
     const bool first = sidx == 0 && p.pre != nullptr;
-    const bool last = sidx + 1 == nstages;
-    const bool to_global = last && !p.comb;
     const Fp* d_hi = p.tw_d + (1u << jh);
     const Fp* d_lo = p.tw_d + (1u << jl);
     const Fp* r_hi = p.tw_r + (1u << jh);
@@ -217,25 +223,29 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
         sym_r_pair(x0, x2, fp_load_ro(r_hi + (pa & mh)));
         sym_r_pair(x1, x3, fp_load_ro(r_hi + (pb & mh)));
       }
-      if (to_global) {
-        if (p.post) {
-          x0 = fp_mul_lazy(x0, fp_load_ro(p.post + (pa & hmask)));
-          x1 = fp_mul_lazy(x1, fp_load_ro(p.post + (pb & hmask)));
-          x2 = fp_mul_lazy(x2, fp_load_ro(p.post + (pc & hmask)));
-          x3 = fp_mul_lazy(x3, fp_load_ro(p.post + (pd & hmask)));
-        }
-        if (gbase + g0 < p.total) fp_store(p.out + gbase + g0, fp_canon(x0));
-        if (gbase + g1 < p.total) fp_store(p.out + gbase + g1, fp_canon(x1));
-        if (gbase + g2 < p.total) fp_store(p.out + gbase + g2, fp_canon(x2));
-        if (gbase + g3 < p.total) fp_store(p.out + gbase + g3, fp_canon(x3));
-      } else {
-        s.st(e0, x0); s.st(e1, x1); s.st(e2, x2); s.st(e3, x3);
-      }
+      s.st(e0, x0); s.st(e1, x1); s.st(e2, x2); s.st(e3, x3);
     }
-    if (!to_global) __syncthreads();
+    __syncthreads();
   }
 
-  if (p.comb) {
+  if (!p.comb) {
+    // store: post-scale (or REDC's h1 = e1 * Z + x * post, one reduction), canonical form, coalesced
+#pragma unroll 1
+    for (uint32_t e = threadIdx.x; e < T; e += NT) {
+      unsigned long long g;
+      uint32_t pos;
+      tm.map(e, g, pos);
+      g += gbase;
+      if (g >= p.total) continue;
+      const uint32_t i = pos & hmask;
+      Fp x = s.ld(e);
+      if (p.E)
+        x = fp_dot2_lazy(fp_load(p.E + ((g << p.e_shift) + p.e_off)), fp_load_ro(p.Z + i), x, fp_load_ro(p.post + i));
+      else if (p.post)
+        x = fp_mul_lazy(x, fp_load_ro(p.post + i));
+      fp_store(p.out + ((g << p.out_shift) + p.out_off), fp_canon(x));
+    }
+  } else {
     // ENTER combine (src/fftree.rs:155-159).  The tile holds the unscaled EXTEND of u at element eu and of
     // v at ev for the same position i; u0, v0 come back from global memory (this CTA's own input
     // when the whole EXTEND ran in this launch, else the depth's input vector).
@@ -311,12 +321,29 @@ static void launch_sym(const SymParams& p, cudaStream_t st) {
 // into the last pass (nvec even: vectors 2w, 2w+1 are u, v of block w); returns false when this depth
 // cannot be fused (the caller then runs EXTEND and the combine kernel separately).
 bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
-                const SymCombine* comb, cudaStream_t st) {
+                const SymCombine* comb, cudaStream_t st, const SymIO* io) {
   const uint32_t LT = sym_log_tile();
   const size_t total = nvec << log_h;
   if (total < 4 || log_h == 0 || log_h > 31) return false;
   if (comb && (nvec & 1)) return false;
+  if (comb && io) throw Error(ERR_INVALID_ARG, "extend_sym: strided views and the fused combine exclude each other");
   SymParams p{};
+  // strided views apply to the first load and the last store; passes in between use a contiguous buffer
+  SymParams first_io{}, last_io{};
+  Fp* mid = out;
+  if (io) {
+    first_io.in_shift = io->in_shift; first_io.in_off = io->in_off;
+    last_io.out_shift = io->out_shift; last_io.out_off = io->out_off;
+    last_io.E = io->E; last_io.Z = io->Z; last_io.e_shift = io->e_shift; last_io.e_off = io->e_off;
+    if (io->E && !(io->Z && post)) throw Error(ERR_INVALID_ARG, "extend_sym: E needs Z and post");
+    mid = io->work;
+  }
+  auto set_first = [&](SymParams& q) { q.in_shift = first_io.in_shift; q.in_off = first_io.in_off; };
+  auto clear_first = [&](SymParams& q) { q.in_shift = 0; q.in_off = 0; };
+  auto set_last = [&](SymParams& q) {
+    q.out_shift = last_io.out_shift; q.out_off = last_io.out_off;
+    q.E = last_io.E; q.Z = last_io.Z; q.e_shift = last_io.e_shift; q.e_off = last_io.e_off;
+  };
   p.tw_d = tw_d;
   p.tw_r = tw_r;
   p.ctr = ctr;
@@ -341,9 +368,12 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
     p.post = comb ? nullptr : post;
     p.comb = comb ? 1 : 0;
     p.nv = 1;
+    set_first(p);
+    set_last(p);
     launch_sym(p, st);
     return true;
   }
+  if (io && !mid) throw Error(ERR_INVALID_ARG, "extend_sym: multi-pass EXTEND with strided views needs a work buffer");
   if (log_h < LT) return false;                     // only reachable for comb with need == LT + 1
   const uint32_t outer = log_h - LT;
   if (comb && outer == 0) return false;             // h == tile: no room for the sibling vector
@@ -355,7 +385,8 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
   p.log_t = LT;
   const Fp* src = in;
   for (uint32_t i = 0; i < npass; i++) {            // outer decompose passes, top levels first
-    p.in = src; p.out = out;
+    p.in = src; p.out = mid;
+    if (i == 0) set_first(p); else clear_first(p);
     p.packed = 0; p.pair = 0; p.comb = 0;
     p.lvl_hi = bounds[i]; p.lvl_lo = bounds[i + 1];
     p.krows = p.lvl_hi - p.lvl_lo; p.log_c = LT - p.krows; p.row_shift = p.lvl_lo; p.boff = p.log_c - p.lvl_lo;
@@ -364,10 +395,11 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
     p.pre = i == 0 ? pre : nullptr;
     p.post = nullptr;
     launch_sym(p, st);
-    src = out;
+    src = mid;
   }
   // inner pass: all levels below the tile size on contiguous tiles
-  p.in = src; p.out = out;
+  p.in = src; p.out = npass == 0 ? out : mid;
+  if (npass == 0) { set_first(p); set_last(p); } else clear_first(p);
   p.packed = 1; p.pair = 0; p.comb = 0; p.nv = 1;
   p.lvl_lo = 0; p.lvl_hi = LT; p.boff = 0; p.do_d = 1; p.do_r = 1;
   p.pre = npass == 0 ? pre : nullptr;
@@ -375,7 +407,8 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
   launch_sym(p, st);
   for (uint32_t i = npass; i-- > 0;) {              // outer recombine passes, top levels last
     const bool fin = i == 0;
-    p.in = out; p.out = (fin && comb) ? comb->out : out;
+    p.in = mid; p.out = (fin && comb) ? comb->out : (fin ? out : mid);
+    if (fin) set_last(p);
     p.packed = 0;
     p.pair = (fin && comb) ? 1 : 0;
     p.comb = p.pair;
