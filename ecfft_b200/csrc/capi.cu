@@ -242,34 +242,48 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
     eng.level_for(n);
     require((coeffs != nullptr && evals != nullptr) || n == 0, ERR_INVALID_ARG, "null buffer");
     Fp* d_out = io.alloc(n);
-    // Large inputs: upload in PARTS chunks on a second stream while the compute stream already enters
-    // the chunks that have landed on the n/PARTS-leaf subtree (the recursion's own split,
-    // src/fftree.rs:150-151); only the first chunk's upload is exposed.  Two halves: smaller chunks
-    // under-fill the GPU (measured: 8 parts cost +6 ms at n = 2^22).
-    const size_t PARTS = 2;
+    // Large inputs: upload in chunks of n/8, n/8, n/4, n/2 coefficients on a second stream while the compute
+    // stream already enters what has landed — chunk g on its own subtree, then the pairwise merges of the
+    // recursion's own split (src/fftree.rs:150-151).  Only the first n/8 upload is exposed; the big chunks
+    // travel while the GPU works on the earlier ones (equal small chunks under-fill the GPU: 8 equal parts
+    // cost +6 ms at n = 2^22).
     if (n >= ((size_t)1 << 16)) {
-      const size_t c = n / PARTS;
+      const size_t c0 = n / 8;
       Fp* d_in = io.alloc(n);
-      Fp* d_mid = io.alloc(n);
+      Fp* bufA = io.alloc(n);
+      Fp* bufB = io.alloc(n / 2);
       cudaStream_t cs = nullptr;
       ECFFT_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      cudaEvent_t ev[PARTS];
+      const size_t off[4] = {0, c0, 2 * c0, 4 * c0}, len[4] = {c0, c0, 2 * c0, 4 * c0};
+      cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
       try {
-        for (size_t g = 0; g < PARTS; g++) {
+        for (int g = 0; g < 4; g++) {
           ECFFT_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
-          ECFFT_CUDA(cudaMemcpyAsync(d_in + g * c, coeffs + 4 * g * c, c * sizeof(Fp), cudaMemcpyHostToDevice, cs));
+          ECFFT_CUDA(cudaMemcpyAsync(d_in + off[g], coeffs + 4 * off[g], len[g] * sizeof(Fp), cudaMemcpyHostToDevice, cs));
           ECFFT_CUDA(cudaEventRecord(ev[g], cs));
-          ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[g], 0));
-          eng.enter_range(d_in + g * c, d_mid + g * c, c, 1, c);
         }
-        eng.enter_range(d_mid, d_out, n, c, n);
+        // chunks 0, 1 -> evaluations on the n/8-leaf subtree (bufA), merged to n/4 (bufB)
+        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[0], 0));
+        eng.enter_range(d_in, bufA, c0, 1, c0);
+        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[1], 0));
+        eng.enter_range(d_in + c0, bufA + c0, c0, 1, c0);
+        eng.enter_range(bufA, bufB, 2 * c0, c0, 2 * c0);
+        // chunk 2 -> n/4-leaf subtree (bufB upper half), merged to n/2 (bufA lower half)
+        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[2], 0));
+        eng.enter_range(d_in + 2 * c0, bufB + 2 * c0, 2 * c0, 1, 2 * c0);
+        eng.enter_range(bufB, bufA, 4 * c0, 2 * c0, 4 * c0);
+        // chunk 3 -> n/2-leaf subtree (bufA upper half), final merge
+        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[3], 0));
+        eng.enter_range(d_in + 4 * c0, bufA + 4 * c0, 4 * c0, 1, 4 * c0);
+        eng.enter_range(bufA, d_out, n, 4 * c0, n);
         io.out(evals, d_out, n);
       } catch (...) {
         cudaStreamSynchronize(cs);
         cudaStreamDestroy(cs);
+        for (int g = 0; g < 4; g++) if (ev[g]) cudaEventDestroy(ev[g]);
         throw;
       }
-      for (size_t g = 0; g < PARTS; g++) cudaEventDestroy(ev[g]);
+      for (int g = 0; g < 4; g++) cudaEventDestroy(ev[g]);
       cudaStreamDestroy(cs);
       return;
     }

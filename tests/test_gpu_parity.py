@@ -315,6 +315,18 @@ def test_full_size_extend_redc_mod(tree22, oracle_mod):
     assert tree22.degree(h) < n // 2
 
 
+def test_host_buffer_enter_pipeline_equals_device_path(tree22, oracle_mod):
+    """ecfft_enter uploads n/8, n/8, n/4, n/2 coefficients on a copy stream and merges the partial ENTERs;
+    every element must equal the single device-resident ENTER (n = 2^17 and 2^20: chunked path)"""
+    import torch
+    for log_n, seed in ((17, 60), (20, 61)):
+        n = 1 << log_n
+        x = oracle_mod.random_elements(n, seed=seed)
+        host = tree22.enter(x)                                                  # numpy in -> host-buffer ABI
+        dev = tree22.enter(torch.from_numpy(x.view(np.int64)).cuda())           # device tensor -> _dev ABI
+        eq(host, dev.cpu().numpy().view(np.uint64))
+
+
 class _ThreadComm:
     """virtual ranks as threads on one device: FIFO mailboxes per (src, dst) pair"""
 
