@@ -172,6 +172,18 @@ def run_reference(args, rank):
     print_json(line)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index`, so that the pinned host buffers of
+    the e2e path are allocated (first touch) on the GPU's NUMA node and PCIe copies do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(index))
+        return f"cpu affinity set to GPU {index}'s NUMA node ({len(os.sched_getaffinity(0))} cpus)"
+    except Exception as e:  # not fatal: the copies are just slower
+        return f"cpu affinity not set ({type(e).__name__})"
+
+
 def _protect_stdout():
     """Libraries (NCCL's version banner, torchrun) write to fd 1; the contract is ONE JSON line on stdout.
     Point fd 1 at stderr for the whole run and return a writer on the original stdout."""
@@ -222,6 +234,7 @@ def main():
         args.warmup = 3
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
@@ -355,6 +368,7 @@ def main():
                 else f"{world} ranks: local ENTER(n/{world}), top {world.bit_length() - 1} depths sharded, straddling butterfly levels and combines read the partner's buffers over NVLink (CUDA-IPC peer memory, flag-ordered), final NCCL all-gather of the result"),
             "inputs": f"{NBUF} rotating coefficient vectors of {n * 32 >> 20} MiB; tables 320 B/leaf resident in HBM; no explicit L2 flush (per-step stream >> 126 MB L2)",
             "tree_build_s": round(t_build, 3),
+            "host": numa,
         },
         "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3,

@@ -136,6 +136,7 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
 void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
              const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st);
+void mg_wait_all(void* const* bases, int world, int rank, unsigned idx, unsigned long long value, unsigned timeout_ms, cudaStream_t st);
 void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st);
 int butterfly_mode();  // ECFFT_B200_BUTTERFLY: 2 = symmetric (default), 1 = normalised, 0 = 2x2 matrices
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
@@ -217,6 +218,7 @@ struct Engine {
 // arena as mapped into this process.  Writes this rank's n/world evaluations (positions
 // [rank n/world, (rank+1) n/world)) to out_chunk.
 static constexpr size_t MG_FLAG_BYTES = 4096;
+static constexpr unsigned MG_DONE_FLAG = MG_FLAG_BYTES / 8 - 1;  // "this rank has finished call `epoch`"
 size_t peer_arena_bytes(size_t n, int world);
 void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int world, void* const* bases,
                 unsigned long long epoch, Fp* out_chunk);

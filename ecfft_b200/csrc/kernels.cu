@@ -461,6 +461,31 @@ __global__ void k_mg_sync(unsigned long long* own_flag, unsigned long long value
   }
   __threadfence_system();
 }
+// all-peers form: spin until flag[idx] of every other rank's arena shows >= value
+struct ArenaBases { const unsigned long long* base[16]; };
+__global__ void k_mg_wait_all(ArenaBases b, int world, int rank, unsigned idx, unsigned long long value, unsigned long long timeout_ns) {
+  unsigned long long t0, t, v;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (int r = 0; r < world; r++) {
+    if (r == rank) continue;
+    for (;;) {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(b.base[r] + idx) : "memory");
+      if (v >= value) break;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+      if (t - t0 > timeout_ns) __trap();
+      __nanosleep(100);
+    }
+  }
+  __threadfence_system();
+}
+void mg_wait_all(void* const* bases, int world, int rank, unsigned idx, unsigned long long value, unsigned timeout_ms, cudaStream_t st) {
+  if (world > 16) throw Error(ERR_INVALID_ARG, "peer schedule supports at most 16 ranks");
+  ArenaBases b{};
+  for (int r = 0; r < world; r++) b.base[r] = (const unsigned long long*)bases[r];
+  k_mg_wait_all<<<1, 1, 0, st>>>(b, world, rank, idx, value, (unsigned long long)timeout_ms * 1000000ull);
+  prof::count_launch();
+  ECFFT_CUDA(cudaGetLastError());
+}
 void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
              const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st) {
   k_mg_sync<<<1, 1, 0, st>>>(own_flag, value, wait_a, wait_b, (unsigned long long)timeout_ms * 1000000ull);

@@ -10,7 +10,9 @@
 // (src/fftree.rs:155-159) reads u0, u1 from the u-vector's rank and v0, v1 from the v-vector's rank.
 // Every buffer a call produces has its own arena slot and all ranks number slots and synchronisation steps
 // alike, so a peer's buffer of the same step sits at the same offset of its arena; ordering is by
-// stream-ordered u64 flags (k::mg_sync).  No host round trip, no send/recv, no collective.
+// stream-ordered u64 flags (k::mg_sync).  A call starts by waiting until every peer has finished the previous
+// call (its reads of this rank's arena included) and ends by publishing that itself has — a device-side
+// barrier.  No host round trip, no send/recv, no collective.
 #include "engine.h"
 
 namespace ecfft {
@@ -50,11 +52,13 @@ void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int worl
   auto slot = [&](int r, size_t idx, size_t off = 0) { return (Fp*)((char*)bases[r] + MG_FLAG_BYTES) + idx * c + off; };
   auto flag = [&](int r, size_t s) { return (unsigned long long*)bases[r] + s; };
   auto sync = [&](int a, int b) {  // publish everything enqueued so far, then wait for the same step of ranks a, b
-    if (sid >= MG_FLAG_BYTES / 8) throw Error(ERR_INVALID_ARG, "peer arena: too many synchronisation steps");
+    if (sid >= MG_DONE_FLAG) throw Error(ERR_INVALID_ARG, "peer arena: too many synchronisation steps");
     k::mg_sync(flag(rank, sid), epoch, a != rank ? flag(a, sid) : nullptr, (b != rank && b != a) ? flag(b, sid) : nullptr, timeout_ms, st);
     sid++;
   };
 
+  // nobody may still be reading this rank's arena from the previous call when it gets overwritten
+  if (epoch > 1) k::mg_wait_all(bases, world, rank, MG_DONE_FLAG, epoch - 1, timeout_ms, st);
   size_t sA = next_slot++;
   eng.enter_range(chunk, slot(rank, sA), c, 1, c);
   int r = 1;
@@ -111,6 +115,7 @@ void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int worl
     k::mg_combine(lv, (size_t)kp * half, slot(usrc, sA, off), slot(vsrc, sA, off), slot(usrc, sW, off), slot(vsrc, sW, off), half, dst, st);
     sA = sNext;
   }
+  k::mg_sync(flag(rank, MG_DONE_FLAG), epoch, nullptr, nullptr, 0, st);  // this rank reads no peer memory any more
 }
 
 }  // namespace ecfft

@@ -137,8 +137,8 @@ def enter_sharded(tree, chunk, n, group=None, gather=True, comm=None):
 # combine kernels load the partner's operands over NVLink themselves (`ecfft_mg_cross_dev`'s partner
 # pointer and `ecfft_mg_combine_dev`'s u/v pointers are peer pointers).  Ordering is by stream-ordered
 # u64 flags in the arenas (`ecfft_mg_signal_dev` / `ecfft_mg_wait_dev`); every produced buffer of one
-# ENTER has its own slot, so within a call there is nothing to protect against overwriting, and the
-# final all-gather (or barrier) of a call orders it before the next one.
+# ENTER has its own slot, so within a call there is nothing to protect against overwriting; a call starts
+# by waiting for every peer's "finished the previous call" flag and ends by publishing its own.
 # ----------------------------------------------------------------------------------------------------
 import ctypes
 
@@ -222,23 +222,21 @@ class PeerArena:
             self.own = None
 
 
-def _finish_peer(out_t, n, world, group, gather, all_gather, barrier):
+def _finish_peer(out_t, n, world, group, gather, all_gather):
+    """calls are ordered against each other on the device (done flags), so gather=False needs no barrier"""
     if gather and world > 1:
         if all_gather is not None:
             return all_gather(out_t)
         full = torch.empty((n, 4), dtype=out_t.dtype, device=out_t.device)
         dist.all_gather_into_tensor(full, out_t, group=group)
         return full
-    # the peers may still be reading this rank's slots: order the call before the next one
-    if world > 1:
-        (barrier or (lambda: dist.barrier(group=group)))()
     return out_t
 
 
-def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gather=None, barrier=None, native=True):
+def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gather=None, native=True):
     """Fully sharded ENTER with peer-memory exchange.  chunk: this rank's n/G coefficients (CUDA tensor).
     Returns the full (n, 4) evaluation vector on every rank (gather=True) or this rank's chunk of it.
-    `all_gather` / `barrier` default to the process group's (tests with virtual ranks pass their own).
+    `all_gather` defaults to the process group's (tests with virtual ranks pass their own).
     native=True runs the whole per-rank schedule inside the library (`ecfft_enter_peer_dev`,
     csrc/sharded.cu); native=False drives the same building blocks step by step from here."""
     L = _lib.load()
@@ -254,7 +252,7 @@ def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gathe
         _lib.check(L.ecfft_enter_peer_dev(tree._h, ctypes.c_void_p(chunk.data_ptr()), n, rank, world, bases, arena.epoch,
                                           ctypes.c_void_p(out_t.data_ptr()),
                                           ctypes.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)))
-        return _finish_peer(out_t, n, world, group, gather, all_gather, barrier)
+        return _finish_peer(out_t, n, world, group, gather, all_gather)
     c = n // world
     log_c = c.bit_length() - 1
     st = ctypes.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)
@@ -272,7 +270,7 @@ def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gathe
         """everything this rank has enqueued is published; then wait for the same step of `peers`"""
         sid = state["sid"]
         state["sid"] += 1
-        if sid >= _FLAG_BYTES // 8:
+        if sid >= _FLAG_BYTES // 8 - 1:
             raise RuntimeError("peer arena: too many synchronisation steps")
         _lib.check(L.ecfft_mg_signal_dev(vp(arena.flag(rank, sid)), epoch, st))
         for p in peers:
@@ -280,6 +278,11 @@ def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gathe
                 _lib.check(L.ecfft_mg_wait_dev(vp(arena.flag(p, sid)), epoch, _WAIT_MS, st))
 
     chunk = chunk.contiguous()
+    done = _FLAG_BYTES // 8 - 1                                 # last flag: "finished call <epoch>"
+    if epoch > 1:                                               # peers may still read this arena from the previous call
+        for p in range(world):
+            if p != rank:
+                _lib.check(L.ecfft_mg_wait_dev(vp(arena.flag(p, done)), epoch - 1, _WAIT_MS, st))
     sA = new_slot()
     _lib.check(L.ecfft_enter_range_dev(h, vp(chunk.data_ptr()), c, 1, c, vp(arena.slot(rank, sA)), st))
     out_t = None
@@ -332,7 +335,8 @@ def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gathe
         sA = sNext
         r *= 2
         m *= 2
+    _lib.check(L.ecfft_mg_signal_dev(vp(arena.flag(rank, done)), epoch, st))
     if out_t is None:                                           # world == 1
         out_t = torch.empty((c, 4), dtype=chunk.dtype, device=chunk.device)
         _lib.check(L.ecfft_enter_range_dev(h, vp(arena.slot(rank, 0)), c, c, c, vp(out_t.data_ptr()), st))
-    return _finish_peer(out_t, n, world, group, gather, all_gather, barrier)
+    return _finish_peer(out_t, n, world, group, gather, all_gather)

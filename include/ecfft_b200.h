@@ -141,8 +141,9 @@ int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned tim
  * coefficient chunk of `rank`, then the top log2(world) depths over peer memory): d_chunk holds this
  * rank's n/world coefficients, arena_bases[r] is rank r's arena as mapped into this process
  * (arena_bases[rank] = this rank's own), epoch must grow by one per call on all ranks alike;
- * d_out_chunk receives evaluations [rank n/world, (rank+1) n/world).  Before the next call the ranks must
- * have passed a barrier or collective (the peers may still be reading this rank's arena). */
+ * d_out_chunk receives evaluations [rank n/world, (rank+1) n/world).  Calls are ordered against each other
+ * on the device: a call first waits until every peer has published the end of the previous one (the last
+ * flag of each arena), so no host barrier is needed between calls. */
 int ecfft_enter_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
                          unsigned long long epoch, void* d_out_chunk, void* stream);
 

@@ -424,15 +424,11 @@ def test_peer_memory_schedule_with_virtual_ranks(trees, oracle_mod, world):
                     barrier.wait()
                     return out
 
-                def bar():
-                    stream.synchronize()
-                    barrier.wait()
-
                 chunk = xd[rank * c:(rank + 1) * c]
-                enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar)
-                full = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar)
-                part = enter_sharded_peer(gpu, chunk, n, arenas[rank], gather=False, all_gather=all_gather, barrier=bar)
-                step = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, barrier=bar, native=False)
+                enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather)
+                full = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather)
+                part = enter_sharded_peer(gpu, chunk, n, arenas[rank], gather=False, all_gather=all_gather)
+                step = enter_sharded_peer(gpu, chunk, n, arenas[rank], all_gather=all_gather, native=False)
                 stream.synchronize()
                 results[rank] = (full.cpu().numpy().view(np.uint64), part.cpu().numpy().view(np.uint64),
                                  step.cpu().numpy().view(np.uint64))
