@@ -379,6 +379,9 @@ def main():
             "kernel": "k_extend_sym", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
             "frac": achieved / peak, "traffic": ncu_traffic(log_n)[0], "traffic_unit": ncu_traffic(log_n)[1],
             "peak_source": peak_src,
+            "note": ("algorithmic bytes of the level-streaming model (SURVEY 8d); the kernel fuses ~10 levels and the combine "
+                     "per HBM round trip, so achieved exceeds the physical peak while `traffic` (ncu DRAM bytes) is ~9x "
+                     "smaller: the kernel is bound by the integer multiplier, see integer_pipe"),
             "kernel_ms_per_step": dom["ms_per_step"], "alg_gb_per_step": dom["alg_gb_per_step"],
             "launches_per_step": dom["launches_per_step"],
             "whole_step": {"alg_gb": alg_bytes_per_elem(log_n) * n / 1e9,
