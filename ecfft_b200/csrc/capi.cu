@@ -242,48 +242,41 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
     eng.level_for(n);
     require((coeffs != nullptr && evals != nullptr) || n == 0, ERR_INVALID_ARG, "null buffer");
     Fp* d_out = io.alloc(n);
-    // Large inputs: upload in chunks of n/8, n/8, n/4, n/2 coefficients on a second stream while the compute
-    // stream already enters what has landed — chunk g on its own subtree, then the pairwise merges of the
-    // recursion's own split (src/fftree.rs:150-151).  Only the first n/8 upload is exposed; the big chunks
-    // travel while the GPU works on the earlier ones (equal small chunks under-fill the GPU: 8 equal parts
-    // cost +6 ms at n = 2^22).
+    // Large inputs: the coefficient vector is uploaded in three chunks (3/16, 5/16, 8/16 of it) on a second
+    // stream and the recursion depths with block size <= 1024 (independent contiguous blocks, one launch per
+    // depth) run on each chunk while the next is still in flight — the chunks grow at the ratio of the
+    // low-depth compute rate to the PCIe rate, so every upload but the first hides behind the previous
+    // chunk's work; the deeper depths run once on the whole vector.  Exposed: the first 3/16 of the upload and
+    // the final download.  Splitting the deeper depths too costs more in extra launches on an under-filled GPU
+    // than it hides (measured at n = 2^22: whole-vector ENTER 15.5 ms, two full half-ENTERs + merge 16.2 ms,
+    // n/8,n/8,n/4,n/2 17.6 ms; tools/pcie_probe.py).
     if (n >= ((size_t)1 << 16)) {
-      const size_t c0 = n / 8;
+      const size_t m_split = 1024;
+      const size_t off[4] = {0, 3 * (n / 16), 8 * (n / 16), n};
       Fp* d_in = io.alloc(n);
-      Fp* bufA = io.alloc(n);
-      Fp* bufB = io.alloc(n / 2);
+      Fp* d_mid = io.alloc(n);
       cudaStream_t cs = nullptr;
       ECFFT_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-      const size_t off[4] = {0, c0, 2 * c0, 4 * c0}, len[4] = {c0, c0, 2 * c0, 4 * c0};
-      cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+      cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
       try {
-        for (int g = 0; g < 4; g++) {
+        for (int g = 0; g < 3; g++) {
           ECFFT_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
-          ECFFT_CUDA(cudaMemcpyAsync(d_in + off[g], coeffs + 4 * off[g], len[g] * sizeof(Fp), cudaMemcpyHostToDevice, cs));
+          ECFFT_CUDA(cudaMemcpyAsync(d_in + off[g], coeffs + 4 * off[g], (off[g + 1] - off[g]) * sizeof(Fp), cudaMemcpyHostToDevice, cs));
           ECFFT_CUDA(cudaEventRecord(ev[g], cs));
         }
-        // chunks 0, 1 -> evaluations on the n/8-leaf subtree (bufA), merged to n/4 (bufB)
-        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[0], 0));
-        eng.enter_range(d_in, bufA, c0, 1, c0);
-        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[1], 0));
-        eng.enter_range(d_in + c0, bufA + c0, c0, 1, c0);
-        eng.enter_range(bufA, bufB, 2 * c0, c0, 2 * c0);
-        // chunk 2 -> n/4-leaf subtree (bufB upper half), merged to n/2 (bufA lower half)
-        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[2], 0));
-        eng.enter_range(d_in + 2 * c0, bufB + 2 * c0, 2 * c0, 1, 2 * c0);
-        eng.enter_range(bufB, bufA, 4 * c0, 2 * c0, 4 * c0);
-        // chunk 3 -> n/2-leaf subtree (bufA upper half), final merge
-        ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[3], 0));
-        eng.enter_range(d_in + 4 * c0, bufA + 4 * c0, 4 * c0, 1, 4 * c0);
-        eng.enter_range(bufA, d_out, n, 4 * c0, n);
+        for (int g = 0; g < 3; g++) {
+          ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[g], 0));
+          eng.enter_range(d_in + off[g], d_mid + off[g], off[g + 1] - off[g], 1, m_split);
+        }
+        eng.enter_range(d_mid, d_out, n, m_split, n);
         io.out(evals, d_out, n);
       } catch (...) {
         cudaStreamSynchronize(cs);
         cudaStreamDestroy(cs);
-        for (int g = 0; g < 4; g++) if (ev[g]) cudaEventDestroy(ev[g]);
+        for (int g = 0; g < 3; g++) if (ev[g]) cudaEventDestroy(ev[g]);
         throw;
       }
-      for (int g = 0; g < 4; g++) cudaEventDestroy(ev[g]);
+      for (int g = 0; g < 3; g++) cudaEventDestroy(ev[g]);
       cudaStreamDestroy(cs);
       return;
     }

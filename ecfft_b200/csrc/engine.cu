@@ -53,8 +53,9 @@ void Engine::extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target)
 // FFTree::enter_impl, src/fftree.rs:143-161, flattened bottom-up: after the pass for m the
 // array holds n/m evaluation vectors of length m (one per coefficient chunk).
 void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
-  if (!is_pow2(n) || !is_pow2(m_lo) || !is_pow2(m_hi)) throw Error(ERR_NOT_POW2, "length is not a power of two");
-  if (m_hi > n || m_lo > m_hi) throw Error(ERR_INVALID_ARG, "enter: bad level range");
+  // n is any whole number of m_hi-blocks (the blocks are independent): a power of two for a full ENTER
+  if (!is_pow2(m_lo) || !is_pow2(m_hi)) throw Error(ERR_NOT_POW2, "length is not a power of two");
+  if (n == 0 || m_hi > n || m_lo > m_hi || n % m_hi) throw Error(ERR_INVALID_ARG, "enter: bad level range");
   level_for(m_hi);
   if (m_lo == m_hi) {
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));

@@ -102,7 +102,8 @@ int ecfft_modular_reduce_dev(const ecfft_tree* t, const void* d_evals, const voi
 int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* d_out, void* stream);
 /* Multi-GPU building block (DESIGN.md "multi-GPU"): run only the bottom-up ENTER recursion
  * depths whose block size m satisfies m_lo < m <= m_hi on an array of n elements that already
- * holds n/m_lo evaluation vectors of length m_lo (m_lo = 1: raw coefficients).  Rank g runs
+ * holds n/m_lo evaluation vectors of length m_lo (m_lo = 1: raw coefficients); n may be any multiple of
+ * m_hi (the blocks are independent).  Rank g runs
  * (1, n/G] on its coefficient chunk, the chunks are all-gathered, then (n/G, n] finishes. */
 int ecfft_enter_range_dev(const ecfft_tree* t, const void* d_in, size_t n, size_t m_lo, size_t m_hi,
                           void* d_out, void* stream);

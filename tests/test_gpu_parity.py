@@ -316,8 +316,9 @@ def test_full_size_extend_redc_mod(tree22, oracle_mod):
 
 
 def test_host_buffer_enter_pipeline_equals_device_path(tree22, oracle_mod):
-    """ecfft_enter uploads n/8, n/8, n/4, n/2 coefficients on a copy stream and merges the partial ENTERs;
-    every element must equal the single device-resident ENTER (n = 2^17 and 2^20: chunked path)"""
+    """ecfft_enter uploads three chunks on a copy stream and runs the low recursion depths on each while the
+    next is in flight; every element must equal the single device-resident ENTER
+    (n = 2^17 and 2^20: pipelined path)"""
     import torch
     for log_n, seed in ((17, 60), (20, 61)):
         n = 1 << log_n
