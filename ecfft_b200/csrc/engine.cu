@@ -3,6 +3,7 @@
 // launch over all sub-problems of that depth (they share the chain level's tables):
 //   ENTER / VANISH run bottom-up, EXIT runs top-down, DEGREE follows its single branch.
 #include <cstdlib>
+#include <utility>
 
 #include "engine.h"
 
@@ -19,6 +20,7 @@ Tree::~Tree() {
   cudaSetDevice(device);
   for (void* p : owned) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
+  for (cudaStream_t s : aux) cudaStreamDestroy(s);
 }
 Fp* Tree::dalloc(size_t count) {
   void* p = nullptr;
@@ -52,11 +54,74 @@ void Engine::extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target)
 
 // FFTree::enter_impl, src/fftree.rs:143-161, flattened bottom-up: after the pass for m the
 // array holds n/m evaluation vectors of length m (one per coefficient chunk).
+// Number of concurrent streams ENTER spreads independent coefficient ranges over (ECFFT_B200_ENTER_STREAMS,
+// default 2): the ranges do not interact below block size n/S, and kernels of different streams fill each
+// other's end-of-launch drain (a launch loses about half a CTA lifetime of SM occupancy while it drains).
+static int enter_streams() {
+  static int s = -1;
+  if (s < 0) {
+    const char* e = getenv("ECFFT_B200_ENTER_STREAMS");
+    s = e ? atoi(e) : 2;
+    if (s != 1 && s != 2 && s != 4) s = 2;
+  }
+  return s;
+}
+cudaStream_t Tree::aux_stream(int i) const {
+  std::lock_guard<std::mutex> lock(aux_mu);
+  while ((int)aux.size() <= i) {
+    cudaStream_t s = nullptr;
+    ECFFT_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    aux.push_back(s);
+  }
+  return aux[i];
+}
+
 void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
   // n is any whole number of m_hi-blocks (the blocks are independent): a power of two for a full ENTER
   if (!is_pow2(m_lo) || !is_pow2(m_hi)) throw Error(ERR_NOT_POW2, "length is not a power of two");
   if (n == 0 || m_hi > n || m_lo > m_hi || n % m_hi) throw Error(ERR_INVALID_ARG, "enter: bad level range");
   level_for(m_hi);
+  if (m_lo == m_hi) {
+    if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    return;
+  }
+  // Independent ranges on concurrent streams: range s runs the depths up to m_mid (the largest block size
+  // that tiles a range) on stream s, the caller's stream joins them and runs the remaining depths.
+  const int S = enter_streams();
+  if (S > 1 && !prof::enabled() && n % (size_t)S == 0 && n / (size_t)S >= ((size_t)1 << 19)) {
+    const size_t part = n / (size_t)S;
+    size_t m_mid = m_hi;
+    while (m_mid > m_lo && part % m_mid) m_mid /= 2;
+    if (m_mid > m_lo) {
+      Fp* mid = m_mid == m_hi ? out : tmp(n);
+      cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
+      ECFFT_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
+      ECFFT_CUDA(cudaEventRecord(fork, st));
+      for (int s = 1; s < S; s++) {
+        cudaStream_t as = t.aux_stream(s - 1);
+        ECFFT_CUDA(cudaStreamWaitEvent(as, fork, 0));
+        Engine sub(t, as);
+        sub.enter_range_serial(in + s * part, mid + s * part, part, m_lo, m_mid);
+        ECFFT_CUDA(cudaEventCreateWithFlags(&join[s], cudaEventDisableTiming));
+        ECFFT_CUDA(cudaEventRecord(join[s], as));
+      }
+      enter_range_serial(in, mid, part, m_lo, m_mid);
+      for (int s = 1; s < S; s++) {
+        ECFFT_CUDA(cudaStreamWaitEvent(st, join[s], 0));
+        cudaEventDestroy(join[s]);
+      }
+      cudaEventDestroy(fork);
+      if (m_mid < m_hi) {
+        enter_range_serial(mid, out, n, m_mid, m_hi);
+        release(mid);
+      }
+      return;
+    }
+  }
+  enter_range_serial(in, out, n, m_lo, m_hi);
+}
+
+void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
   if (m_lo == m_hi) {
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
@@ -185,10 +250,46 @@ void Engine::exit(const Fp* evals, Fp* out, size_t n) const {
   Fp* nxt = tmp(n);
   Fp* M = tmp(n);
   ECFFT_CUDA(cudaMemcpyAsync(cur, evals, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
-  for (size_t m = n; m >= 2; m /= 2) {
+  // After the pass for block size m the array holds independent vectors of length m/2, so once the first
+  // depth is done the two halves of the array run on two streams (their kernels fill each other's
+  // end-of-launch drain, as in enter_range).
+  const bool fork = enter_streams() > 1 && !prof::enabled() && n >= ((size_t)1 << 20);
+  exit_depths(cur, nxt, M, n, n, fork ? n / 2 : 1);
+  if (fork) {
+    const size_t part = n / 2;
+    std::swap(cur, nxt);  // exit_depths left the result of its single pass in the second buffer
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    ECFFT_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    ECFFT_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    ECFFT_CUDA(cudaEventRecord(ev_fork, st));
+    cudaStream_t as = t.aux_stream(0);
+    ECFFT_CUDA(cudaStreamWaitEvent(as, ev_fork, 0));
+    Engine sub(t, as);
+    const bool odd_a = sub.exit_depths(cur + part, nxt + part, M + part, part, part, 1);
+    ECFFT_CUDA(cudaEventRecord(ev_join, as));
+    const bool odd_b = exit_depths(cur, nxt, M, part, part, 1);
+    ECFFT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
+    cudaEventDestroy(ev_fork);
+    cudaEventDestroy(ev_join);
+    (void)odd_a;
+    if (odd_b) std::swap(cur, nxt);  // both halves run the same number of passes
+  } else if (ilog2(n) & 1) {
+    std::swap(cur, nxt);
+  }
+  ECFFT_CUDA(cudaMemcpyAsync(out, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+  release(cur);
+  release(nxt);
+  release(M);
+}
+
+// The passes of EXIT for block sizes m_from, m_from/2, ..., 2*m_stop on an array of len elements (len/m
+// vectors per pass), ping-ponging between cur and nxt.  Returns true when the result ended up in nxt.
+bool Engine::exit_depths(Fp* cur, Fp* nxt, Fp* M, size_t len, size_t m_from, size_t m_stop) const {
+  bool in_nxt = false;
+  for (size_t m = m_from; m >= 2 && m > m_stop; m /= 2) {
     const Level& lv = level_for(m);
     if (!lv.z0z0) throw Error(ERR_MISSING_TABLES, "exit: tree was built without the Z tables");
-    const size_t h = m / 2, nvec = n / m;
+    const size_t h = m / 2, nvec = len / m;
     // the reference batch-inverts xnn_s[::2] on every call (fftree.rs:235); the stored
     // xnn_s_inv holds the same values
     Fp* a0inv = tmp(h);
@@ -196,14 +297,10 @@ void Engine::exit(const Fp* evals, Fp* out, size_t n) const {
     modular_reduce(cur, lv.xnn_s, a0inv, lv.z0z0, m, nvec, M);
     k::exit_split(nxt, cur, M, lv.xnn_s_inv, h, nvec, st);
     release(a0inv);
-    Fp* sw = cur;
-    cur = nxt;
-    nxt = sw;
+    std::swap(cur, nxt);
+    in_nxt = !in_nxt;
   }
-  ECFFT_CUDA(cudaMemcpyAsync(out, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
-  release(cur);
-  release(nxt);
-  release(M);
+  return in_nxt;
 }
 
 // FFTree::mextend_impl, src/fftree.rs:128-135

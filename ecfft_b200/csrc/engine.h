@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -94,6 +95,9 @@ struct Tree {
   Fp base_leaf0, base_leaf1;         // leaves of the 2-leaf chain level (VANISH base case, fftree.rs:293-298)
   cudaStream_t stream = nullptr;     // default stream for host-buffer calls
   std::vector<void*> owned;          // device allocations to free
+  mutable std::vector<cudaStream_t> aux;  // helper streams ENTER forks independent ranges onto (engine.cu)
+  mutable std::mutex aux_mu;
+  cudaStream_t aux_stream(int i) const;
   ~Tree();
   Fp* dalloc(size_t count);          // owned device allocation of `count` Fp
   size_t n() const { return (size_t)1 << log_n; }
@@ -204,8 +208,10 @@ struct Engine {
 
   // the FFTree<F> surface (fftree.rs:72-316) on device buffers
   void enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // bottom-up levels m_lo < m <= m_hi
+  void enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // ... on this engine's stream only
   void enter(const Fp* coeffs, Fp* out, size_t n) const { enter_range(coeffs, out, n, 1, n); }
   void exit(const Fp* evals, Fp* out, size_t n) const;
+  bool exit_depths(Fp* cur, Fp* nxt, Fp* M, size_t len, size_t m_from, size_t m_stop) const;
   void mextend(const Fp* in, Fp* out, size_t h, Moiety target, DataForm form) const;
   size_t degree(const Fp* evals, size_t n) const;
   void redc_user(const Fp* evals, const Fp* a_mont, size_t n, Moiety moiety, Fp* out) const;

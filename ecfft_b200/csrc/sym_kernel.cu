@@ -272,17 +272,18 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
 }
 
 // Launch shapes (ECFFT_B200_SYM_VARIANT): 0 = 128 threads, 5 CTAs/SM, 1024-element tile (default);
-// 1 = 128 threads, 4 CTAs/SM; 2 = 256 threads, 3 CTAs/SM; 3 = 256 threads, 2 CTAs/SM, 2048-element tile.
+// 1 = 128 threads, 4 CTAs/SM; 2 = 256 threads, 3 CTAs/SM; 3 = 256 threads, 2 CTAs/SM, 2048-element tile;
+// 4 = 64 threads, 10 CTAs/SM, 512-element tile (shorter CTAs: smaller end-of-launch drain, one level less per pass).
 static int sym_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ECFFT_B200_SYM_VARIANT");
     v = e ? atoi(e) : 0;
-    if (v < 0 || v > 3) v = 0;
+    if (v < 0 || v > 4) v = 0;
   }
   return v;
 }
-static uint32_t sym_log_tile() { return sym_variant() == 3 ? 11 : 10; }
+static uint32_t sym_log_tile() { return sym_variant() == 3 ? 11 : sym_variant() == 4 ? 9 : 10; }
 
 template <int NT, int MINB>
 static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
@@ -310,6 +311,7 @@ static void launch_sym(const SymParams& p, cudaStream_t st) {
     case 1: launch_shape<128, 4>(p, tiles, st); break;
     case 2: launch_shape<256, 3>(p, tiles, st); break;
     case 3: launch_shape<256, 2>(p, tiles, st); break;
+    case 4: launch_shape<64, 10>(p, tiles, st); break;
     default: launch_shape<128, 5>(p, tiles, st); break;
   }
   if (timed) prof::record_end(st);
