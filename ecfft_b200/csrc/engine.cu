@@ -66,6 +66,17 @@ static int enter_streams() {
   }
   return s;
 }
+// smallest range (elements per stream) worth a stream of its own (ECFFT_B200_ENTER_FORK_MIN = log2, default 19)
+static size_t enter_fork_min() {
+  static size_t v = 0;
+  if (!v) {
+    const char* e = getenv("ECFFT_B200_ENTER_FORK_MIN");
+    int lg = e ? atoi(e) : 19;
+    if (lg < 10 || lg > 40) lg = 19;
+    v = (size_t)1 << lg;
+  }
+  return v;
+}
 cudaStream_t Tree::aux_stream(int i) const {
   std::lock_guard<std::mutex> lock(aux_mu);
   while ((int)aux.size() <= i) {
@@ -88,7 +99,7 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
   // Independent ranges on concurrent streams: range s runs the depths up to m_mid (the largest block size
   // that tiles a range) on stream s, the caller's stream joins them and runs the remaining depths.
   const int S = enter_streams();
-  if (S > 1 && !prof::enabled() && n % (size_t)S == 0 && n / (size_t)S >= ((size_t)1 << 19)) {
+  if (S > 1 && !prof::enabled() && n % (size_t)S == 0 && n / (size_t)S >= enter_fork_min()) {
     const size_t part = n / (size_t)S;
     size_t m_mid = m_hi;
     while (m_mid > m_lo && part % m_mid) m_mid /= 2;
