@@ -77,6 +77,15 @@ static size_t enter_fork_min() {
   }
   return v;
 }
+namespace {
+struct ScopedEvent {  // cudaEventDestroy defers the release until the recorded work has completed
+  cudaEvent_t e = nullptr;
+  ScopedEvent() { ECFFT_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); }
+  ~ScopedEvent() { if (e) cudaEventDestroy(e); }
+  ScopedEvent(const ScopedEvent&) = delete;
+  ScopedEvent& operator=(const ScopedEvent&) = delete;
+};
+}  // namespace
 cudaStream_t Tree::aux_stream(int i) const {
   std::lock_guard<std::mutex> lock(aux_mu);
   while ((int)aux.size() <= i) {
@@ -105,23 +114,17 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
     while (m_mid > m_lo && part % m_mid) m_mid /= 2;
     if (m_mid > m_lo) {
       Fp* mid = m_mid == m_hi ? out : tmp(n);
-      cudaEvent_t fork = nullptr, join[4] = {nullptr, nullptr, nullptr, nullptr};
-      ECFFT_CUDA(cudaEventCreateWithFlags(&fork, cudaEventDisableTiming));
-      ECFFT_CUDA(cudaEventRecord(fork, st));
+      ScopedEvent fork, join[3];
+      ECFFT_CUDA(cudaEventRecord(fork.e, st));
       for (int s = 1; s < S; s++) {
         cudaStream_t as = t.aux_stream(s - 1);
-        ECFFT_CUDA(cudaStreamWaitEvent(as, fork, 0));
+        ECFFT_CUDA(cudaStreamWaitEvent(as, fork.e, 0));
         Engine sub(t, as);
         sub.enter_range_serial(in + s * part, mid + s * part, part, m_lo, m_mid);
-        ECFFT_CUDA(cudaEventCreateWithFlags(&join[s], cudaEventDisableTiming));
-        ECFFT_CUDA(cudaEventRecord(join[s], as));
+        ECFFT_CUDA(cudaEventRecord(join[s - 1].e, as));
       }
       enter_range_serial(in, mid, part, m_lo, m_mid);
-      for (int s = 1; s < S; s++) {
-        ECFFT_CUDA(cudaStreamWaitEvent(st, join[s], 0));
-        cudaEventDestroy(join[s]);
-      }
-      cudaEventDestroy(fork);
+      for (int s = 1; s < S; s++) ECFFT_CUDA(cudaStreamWaitEvent(st, join[s - 1].e, 0));
       if (m_mid < m_hi) {
         enter_range_serial(mid, out, n, m_mid, m_hi);
         release(mid);
@@ -269,20 +272,15 @@ void Engine::exit(const Fp* evals, Fp* out, size_t n) const {
   if (fork) {
     const size_t part = n / 2;
     std::swap(cur, nxt);  // exit_depths left the result of its single pass in the second buffer
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
-    ECFFT_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
-    ECFFT_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
-    ECFFT_CUDA(cudaEventRecord(ev_fork, st));
+    ScopedEvent ev_fork, ev_join;
+    ECFFT_CUDA(cudaEventRecord(ev_fork.e, st));
     cudaStream_t as = t.aux_stream(0);
-    ECFFT_CUDA(cudaStreamWaitEvent(as, ev_fork, 0));
+    ECFFT_CUDA(cudaStreamWaitEvent(as, ev_fork.e, 0));
     Engine sub(t, as);
-    const bool odd_a = sub.exit_depths(cur + part, nxt + part, M + part, part, part, 1);
-    ECFFT_CUDA(cudaEventRecord(ev_join, as));
+    sub.exit_depths(cur + part, nxt + part, M + part, part, part, 1);
+    ECFFT_CUDA(cudaEventRecord(ev_join.e, as));
     const bool odd_b = exit_depths(cur, nxt, M, part, part, 1);
-    ECFFT_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
-    cudaEventDestroy(ev_fork);
-    cudaEventDestroy(ev_join);
-    (void)odd_a;
+    ECFFT_CUDA(cudaStreamWaitEvent(st, ev_join.e, 0));
     if (odd_b) std::swap(cur, nxt);  // both halves run the same number of passes
   } else if (ilog2(n) & 1) {
     std::swap(cur, nxt);
