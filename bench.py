@@ -416,6 +416,9 @@ def main():
     if rank == 0:
         print_json(line)
     if world > 1:
+        if args.multi_gpu == "peer":
+            dist.barrier()          # nobody reads a peer arena any more
+            arena.close()
         dist.destroy_process_group()
 
 
