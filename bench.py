@@ -164,7 +164,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64x4 Montgomery (ark-ff layout)", "data": "synthetic",
-        "config": {"workload": f"secp256k1::Fp ENTER n=2^{log_n} (CPU oracle port of the reference, bounded sample)"},
+        "config": {"workload": f"secp256k1::Fp ENTER n=2^{log_n} (full log^2 recursion) on a 2^{log_n}-leaf FFTree",
+                   "implementation": "CPU restatement of the reference (oracle/, C, all host threads); each step is a bounded sample, see cpu_baseline.sample"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
