@@ -503,6 +503,21 @@ int ecfft_mg_arena_close(void* d_peer_ptr) {
 int ecfft_mg_arena_free(void* d_ptr) {
   return guard([&] { ECFFT_CUDA(cudaFree(d_ptr)); });
 }
+int ecfft_selftest_field(int device, unsigned long long samples, unsigned long long* counters3) {
+  return guard([&] {
+    require(counters3 != nullptr, ERR_INVALID_ARG, "null output");
+    ECFFT_CUDA(cudaSetDevice(device));
+    unsigned long long* d = nullptr;
+    ECFFT_CUDA(cudaMalloc((void**)&d, 3 * sizeof(unsigned long long)));
+    cudaError_t e = cudaMemset(d, 0, 3 * sizeof(unsigned long long));
+    if (e == cudaSuccess) {
+      k::selftest_field(d, samples, nullptr);
+      e = cudaMemcpy(counters3, d, 3 * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    }
+    cudaFree(d);
+    ECFFT_CUDA(e);
+  });
+}
 int ecfft_mg_arena_bytes(size_t n, int world, size_t* bytes) {
   return guard([&] {
     require(bytes != nullptr, ERR_INVALID_ARG, "null output");

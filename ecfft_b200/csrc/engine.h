@@ -185,7 +185,8 @@ void fold_sumform_prescale(Fp* gami, const Fp* f_top, size_t fstride, size_t h, 
 // symmetric-form tables; beta_by_j[j] is the fixed point of the map used by the level with half-stride 2^j
 void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st);
 void build_gamma_sym(Fp* gam, const Fp* rmat, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st);
-void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st);  // out[i] = a[i]*b[b_off + i*b_stride]
+void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st);
+void selftest_field(unsigned long long* counters3, unsigned long long samples, cudaStream_t st);  // device self-test of the lazy add/sub forms  // out[i] = a[i]*b[b_off + i*b_stride]
 }  // namespace k
 
 // ---- engine.cu: the algorithms on device buffers ------------------------------------------

@@ -589,6 +589,82 @@ void build_gamma_sym(Fp* gam, const Fp* rmat, const Fp* f_top, size_t fstride, s
     fp_store(gam + p, fp_canon(acc));
   });
 }
+// ------------------------------------------------------------------------------------------
+// Device self-test of the lazy add / subtract forms the butterflies use (fp_add_lazy_f, fp_sub_lazy2_f and
+// their branch-free siblings): directed operands that drive the carry out of the low two limbs ("ripple")
+// and the second wrap, compared with canonical arithmetic on the canonicalised operands.  The host build of
+// fp.cuh is fuzzed the same way (tests/test_fp_host.py); this runs the inline-PTX carry chains themselves.
+// counters: [0] mismatches, [1] additions that took the ripple path, [2] subtractions that did.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long selftest_mix(unsigned long long& x) {
+  x += 0x9E3779B97F4A7C15ull;
+  unsigned long long z = x;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ Fp selftest_wrap_sub(const Fp& a, const Fp& b) {  // a - b mod 2^256
+  Fp d;
+  d.v[0] = sub_cc(a.v[0], b.v[0]);
+#pragma unroll
+  for (int i = 1; i < 8; i++) d.v[i] = subc_cc(a.v[i], b.v[i]);
+  return d;
+}
+__global__ void __launch_bounds__(256) k_selftest_addsub(unsigned long long* counters, unsigned long long n) {
+  for (unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long)gridDim.x * blockDim.x) {
+    unsigned long long st = t * 0x2545F4914F6CDD1Dull + 12345;
+    Fp a, tgt;
+    for (int i = 0; i < 4; i++) {
+      unsigned long long r = selftest_mix(st), q = selftest_mix(st);
+      a.v[2 * i] = (uint32_t)r; a.v[2 * i + 1] = (uint32_t)(r >> 32);
+      tgt.v[2 * i] = (uint32_t)q; tgt.v[2 * i + 1] = (uint32_t)(q >> 32);
+    }
+    const unsigned kind = (unsigned)(t % 6);
+    const unsigned long long small = selftest_mix(st) >> (31 + (selftest_mix(st) & 31));  // 1..33 significant bits
+    if (kind == 0 || kind == 1) {        // wrapped sum with low 64 bits within DELTA of 2^64 (kind 1: high limbs all ones)
+      const unsigned long long lo = ~0ull - small;
+      tgt.v[0] = (uint32_t)lo; tgt.v[1] = (uint32_t)(lo >> 32);
+      if (kind == 1) for (int i = 2; i < 8; i++) tgt.v[i] = 0xFFFFFFFFu;
+    } else if (kind == 2 || kind == 3) { // borrowed difference with low 64 bits below DELTA (kind 3: high limbs zero)
+      tgt.v[0] = (uint32_t)small; tgt.v[1] = (uint32_t)(small >> 32);
+      if (kind == 3) for (int i = 2; i < 8; i++) tgt.v[i] = 0u;
+    } else if (kind == 4) {              // operands near 2^256
+      for (int i = 2; i < 8; i++) a.v[i] = 0xFFFFFFFFu;
+    }
+    // kinds 0,1: b = tgt - a (so a + b = tgt mod 2^256); kinds 2,3: b = a - tgt (so a - b = tgt mod 2^256)
+    const Fp b = (kind <= 1) ? selftest_wrap_sub(tgt, a) : (kind <= 3 ? selftest_wrap_sub(a, tgt) : tgt);
+    const Fp ac = fp_canon(a), bc = fp_canon(b);
+    const Fp want_add = fp_add(ac, bc), want_sub = fp_sub(ac, bc);
+    unsigned long long bad = 0;
+    bad += !fp_eq(fp_canon(fp_add_lazy_f(a, b)), want_add);
+    bad += !fp_eq(fp_canon(fp_add_lazy(a, b)), want_add);
+    bad += !fp_eq(fp_canon(fp_sub_lazy2_f(a, b)), want_sub);
+    bad += !fp_eq(fp_canon(fp_sub_lazy2(a, b)), want_sub);
+    if (bad) atomicAdd(counters, bad);
+    // did this sample take the ripple paths?  (carry/borrow out of the low two limbs after the DELTA fold)
+    {
+      Fp s;
+      s.v[0] = add_cc(a.v[0], b.v[0]);
+#pragma unroll
+      for (int i = 1; i < 8; i++) s.v[i] = addc_cc(a.v[i], b.v[i]);
+      const uint32_t c = addc(0u, 0u);
+      const unsigned long long lo = ((unsigned long long)s.v[1] << 32) | s.v[0];
+      if (c && lo + 0x1000003D1ull < lo) atomicAdd(counters + 1, 1ull);
+      const Fp d = selftest_wrap_sub(a, b);
+      bool borrow = false;  // a < b as 256-bit integers
+      for (int i = 7; i >= 0; i--) {
+        if (a.v[i] != b.v[i]) { borrow = a.v[i] < b.v[i]; break; }
+      }
+      const unsigned long long dlo = ((unsigned long long)d.v[1] << 32) | d.v[0];
+      if (borrow && dlo < 0x1000003D1ull) atomicAdd(counters + 2, 1ull);
+    }
+  }
+}
+void selftest_field(unsigned long long* counters, unsigned long long n, cudaStream_t st) {
+  k_selftest_addsub<<<148 * 8, 256, 0, st>>>(counters, n);
+  prof::count_launch();
+  ECFFT_CUDA(cudaGetLastError());
+}
 void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st) {
   map(n, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_load(a + i), fp_load(b + b_off + i * b_stride))); });
 }

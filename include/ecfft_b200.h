@@ -148,6 +148,12 @@ int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned tim
 int ecfft_enter_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
                          unsigned long long epoch, void* d_out_chunk, void* stream);
 
+/* Device self-test of the field routines the butterflies use for a + b and a - b on unreduced operands
+ * (the replacement of ark-ff's add/sub at src/utils.rs:341-346): `samples` directed operand pairs that
+ * drive the rare carry paths, checked on the GPU against canonical arithmetic.
+ * counters3 = { mismatches, additions that took the rare path, subtractions that did }. */
+int ecfft_selftest_field(int device, unsigned long long samples, unsigned long long* counters3);
+
 /* ---- instrumentation used by bench.py ------------------------------------------------- */
 /* kernels launched by this library since it was loaded */
 unsigned long long ecfft_launch_count(void);

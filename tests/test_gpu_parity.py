@@ -328,6 +328,19 @@ def test_host_buffer_enter_pipeline_equals_device_path(tree22, oracle_mod):
         eq(host, dev.cpu().numpy().view(np.uint64))
 
 
+def test_device_field_selftest_drives_the_rare_carry_paths():
+    """fp_add_lazy_f / fp_sub_lazy2_f branch on a carry out of the low two limbs (probability ~2^-31 on random
+    data, i.e. about once per ENTER(2^22)): directed operands on the device itself, against canonical
+    arithmetic — and proof that the rare paths were taken."""
+    import ctypes
+    from ecfft_b200 import _lib
+    counters = (ctypes.c_ulonglong * 3)()
+    _lib.check(_lib.load().ecfft_selftest_field(0, 6 << 20, counters))
+    mismatches, add_ripples, sub_ripples = counters[0], counters[1], counters[2]
+    assert mismatches == 0
+    assert add_ripples > 100000 and sub_ripples > 100000
+
+
 class _ThreadComm:
     """virtual ranks as threads on one device: FIFO mailboxes per (src, dst) pair"""
 
