@@ -6,12 +6,16 @@
 One JSON line on stdout (rank 0).  A step = one ENTER of n synthetic random coefficients.
   value : evals/s with input and output resident in HBM (CUDA events, max over ranks)
   e2e   : the same through the host-buffer C ABI call (pinned host in -> H2D -> ENTER -> D2H)
-  roofline : the dominant kernel (k_extend_sym) against the measured HBM peak, using the
-             ALGORITHMIC bytes of the level-streaming model (DESIGN.md / SURVEY.md 8d); the kernel fuses
-             ~10 levels per HBM round trip, so `achieved` exceeds the physical peak and `traffic` (ncu)
-             is ~10x smaller; `integer_pipe` reports the pipe that actually binds it
+  roofline : the dominant kernel against the measured HBM peak, using the ALGORITHMIC bytes of the
+             level-streaming model (DESIGN.md / SURVEY.md 8d); the kernel fuses ~10 levels per HBM round trip,
+             so `achieved` exceeds the physical peak and `traffic` (ncu) is ~10x smaller; the flat
+             `integer_pipe_frac` reports the pipe that actually binds it
   cpu_baseline : the CPU oracle (single thread, like the reference library) on a bounded sample
---impl reference times the CPU restatement of the reference (oracle/, all host threads).
+  cfg_* : the other BASELINE.json configurations, timed in the same run (flat keys):
+          N = 1: ENTER->EXIT round trip 2^12, EXTEND 2^20, REDC / MOD 2^20, EXIT 2^22
+          N > 1: ENTER 2^24 sharded over the N GPUs; every rank checks the sharded results (2^22 and 2^24)
+                 bit for bit against a single-GPU ENTER of the whole vector on its own device
+--impl reference times the CPU restatement of the reference (oracle/, all host threads) at the same n.
 """
 import argparse
 import ctypes
@@ -59,13 +63,15 @@ def ncu_traffic(log_n):
     """DRAM bytes the dominant kernel moved per step in the committed ncu capture (profiles/), n = 2^22 only"""
     if log_n != 22:
         return None, None
-    try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
-            t = json.load(f)
-        k = t.get("k_extend_sym") or t["k_extend_tile"]
-        return k["dram_total_gb_per_step"], f"GB per step over {k['launches_per_step']} launches (profiles/r01_traffic.json; algorithmic bytes are per step too)"
-    except Exception:
-        return None, None
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)
+            k = t.get("k_enter_flow") or t.get("k_extend_sym") or t["k_extend_tile"]
+            return k["dram_total_gb_per_step"], f"GB per step over {k['launches_per_step']} launches (profiles/{name}; algorithmic bytes are per step too)"
+        except Exception:
+            continue
+    return None, None
 
 
 def measured_peak():
@@ -89,7 +95,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
@@ -127,7 +133,7 @@ def cpu_sample(log_n_sample, log_n_target, threads):
     """time the oracle's ENTER on a bounded sample and scale by modmul count to the target size"""
     from oracle import oracle as O
     ns = 1 << log_n_sample
-    tree = O.OracleTree.build(ns, parts=1)
+    tree = O.OracleTree.build(ns, parts=1, threads=os.cpu_count() or 1)
     x = O.random_elements(ns, seed=1)
     t0 = time.perf_counter()
     out = tree.enter(x, threads=threads)
@@ -140,15 +146,18 @@ def cpu_sample(log_n_sample, log_n_target, threads):
 
 def run_reference(args, rank):
     """--impl reference: the reference's CPU implementation.  The Rust crate cannot be compiled in this
-    image (no cargo/rustc, arkworks not vendored), so this is the C restatement under oracle/ ("port")."""
+    image (no cargo/rustc, arkworks not vendored), so this is the C restatement under oracle/ ("port"),
+    run at the SAME n as the GPU arm: every step is one whole ENTER(n) on all host threads."""
     if rank != 0:
         return
     log_n = args.log_n
     threads = os.cpu_count() or 1
-    log_s = min(log_n, args.ref_sample_log_n)
+    log_s = log_n if args.ref_sample_log_n is None else min(log_n, args.ref_sample_log_n)
     from oracle import oracle as O
     ns = 1 << log_s
-    tree = O.OracleTree.build(ns, parts=1)
+    t_build = time.perf_counter()
+    tree = O.OracleTree.build(ns, parts=1, threads=threads)
+    t_build = time.perf_counter() - t_build
     x = O.random_elements(ns, seed=1)
     for _ in range(args.warmup):
         tree.enter(x, threads=threads)
@@ -158,14 +167,18 @@ def run_reference(args, rank):
     dt = (time.perf_counter() - t0) / args.steps
     scale = (modmuls_per_elem(log_n) * (1 << log_n)) / (modmuls_per_elem(log_s) * ns)
     value = (1 << log_n) / (dt * scale)
-    sample = (f"each step = ENTER n=2^{log_s} on {threads} threads ({dt:.3f} s), scaled by field-multiplication "
-              f"count x{scale:.1f} to n=2^{log_n}")
+    if log_s == log_n:
+        sample = f"each step = one whole ENTER n=2^{log_n} on {threads} threads ({dt:.3f} s per step, measured, not extrapolated)"
+    else:
+        sample = (f"each step = ENTER n=2^{log_s} on {threads} threads ({dt:.3f} s), scaled by field-multiplication "
+                  f"count x{scale:.1f} to n=2^{log_n}")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "u64x4 Montgomery (ark-ff layout)", "data": "synthetic",
         "config": {"workload": f"secp256k1::Fp ENTER n=2^{log_n} (full log^2 recursion) on a 2^{log_n}-leaf FFTree",
-                   "implementation": "CPU restatement of the reference (oracle/, C, all host threads); each step is a bounded sample, see cpu_baseline.sample"},
+                   "implementation": "CPU restatement of the reference (oracle/, C, all host threads)",
+                   "tree_build_s": round(t_build, 1)},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -205,8 +218,10 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--log-n", type=int, default=22)
     ap.add_argument("--cpu-sample-log-n", type=int, default=18)
-    ap.add_argument("--ref-sample-log-n", type=int, default=18)
+    ap.add_argument("--ref-sample-log-n", type=int, default=None,
+                    help="reference arm: time ENTER at this smaller size and scale (default: the real n, measured)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg_* timings of the other BASELINE configurations")
     ap.add_argument("--multi-gpu", default="peer", choices=["peer", "sharded", "allgather"],
                     help="top-depth schedule for N>1: sharded with the kernels reading the partner's buffers over NVLink "
                          "(peer, default), sharded with NCCL send/recv per straddling level, or one all-gather + replicated top depths")
@@ -256,11 +271,14 @@ def main():
     chunk = n // world
     dev_in = [h[rank * chunk:(rank + 1) * chunk].to(dev) for h in host_in]
 
+    arena = None
     if world > 1 and args.multi_gpu == "peer":
         arena = PeerArena.create(n, local_rank)
-        shard_fn = lambda tree_, x_, n_: enter_sharded_peer(tree_, x_, n_, arena)
+        shard_fn = lambda tree_, x_, n_, **kw: enter_sharded_peer(tree_, x_, n_, arena, **kw)
+    elif args.multi_gpu == "allgather":
+        shard_fn = lambda tree_, x_, n_, **kw: enter_sharded_allgather(tree_, x_, n_)
     else:
-        shard_fn = enter_sharded_allgather if args.multi_gpu == "allgather" else enter_sharded
+        shard_fn = enter_sharded
 
     def step(i):
         x = dev_in[i % NBUF]
@@ -280,23 +298,50 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- timed region: K steps, device-resident input and output --------------------------------
-    barrier()
-    launches0 = L.ecfft_launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        out = step(i)
-    e1.record()
-    barrier()
-    ms = e0.elapsed_time(e1)
-    launches = L.ecfft_launch_count() - launches0
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms_per_step = ms / args.steps
+        return float(t.item())
+
+    def all_ranks_true(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device=dev, dtype=torch.int32)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
+
+    def timed(fn, steps):
+        """K calls bracketed by barrier + synchronize on both sides, CUDA events, max over ranks -> ms per call"""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    # ---- timed region: K steps, device-resident input and output --------------------------------
+    launches0 = L.ecfft_launch_count()
+    ms_per_step = timed(step, args.steps)
+    launches = L.ecfft_launch_count() - launches0
     value = n / (ms_per_step * 1e-3)
+    extra = {}
+
+    # ---- N > 1: the sharded result against a single-GPU ENTER of the whole vector, on every rank ----
+    if world > 1:
+        full_x = host_in[0].to(dev)
+        want = tree.enter(full_x)
+        got = shard_fn(tree, dev_in[0], n)
+        ok = bool((got == want).all())
+        del full_x, want, got
+        extra["multi_gpu_matches_single"] = all_ranks_true(ok)
+        if args.multi_gpu != "allgather":   # the final all-gather's share of the step
+            ms_nogather = timed(lambda i: shard_fn(tree, dev_in[i % NBUF], n, gather=False), args.steps)
+            extra["allgather_ms_per_step"] = ms_per_step - ms_nogather
+            extra["ms_per_step_without_final_allgather"] = ms_nogather
 
     # ---- roofline of the dominant kernel: same steps with per-launch CUDA events ---------------------
     L.ecfft_profile_enable(1)
@@ -331,32 +376,35 @@ def main():
         h2d = d2h = n * 32
         last_e2e_in = (args.steps - 1) % NBUF
     else:
-        # every rank uploads its n/N coefficients from pinned memory and downloads its n/N evaluations (rank r's
-        # slice of the result vector) into pinned memory: the host-side result is sharded like the input
+        # every rank uploads its n/N coefficients from pinned memory, the ranks run the sharded ENTER, and EVERY
+        # rank downloads the WHOLE evaluation vector into its own pinned memory (the reference returns a whole
+        # Vec<F>); the variant where the host-side result stays sharded is reported as e2e_sharded_ms_per_step
         host_chunks = [h[rank * chunk:(rank + 1) * chunk] for h in host_in]
-        host_out = torch.empty((chunk, 4), dtype=torch.int64).pin_memory()
-        if args.multi_gpu == "peer":
-            e2e_fn = lambda x_: enter_sharded_peer(tree, x_, n, arena, gather=False)
-        elif args.multi_gpu == "sharded":
-            e2e_fn = lambda x_: enter_sharded(tree, x_, n, gather=False)
-        else:
-            e2e_fn = lambda x_: enter_sharded_allgather(tree, x_, n)[rank * chunk:(rank + 1) * chunk]
-        for i in range(2):
-            host_out.copy_(e2e_fn(host_chunks[i % NBUF].to(dev, non_blocking=True)), non_blocking=True)
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(args.steps):
-            xd = host_chunks[i % NBUF].to(dev, non_blocking=True)
-            host_out.copy_(e2e_fn(xd), non_blocking=True)
-            torch.cuda.synchronize()
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / args.steps
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-        h2d, d2h = chunk * 32, chunk * 32
+
+        def e2e_loop(gather):
+            host_out = torch.empty((n if gather else chunk, 4), dtype=torch.int64).pin_memory()
+            if args.multi_gpu == "allgather":
+                fn = (lambda x_: enter_sharded_allgather(tree, x_, n)) if gather else (lambda x_: enter_sharded_allgather(tree, x_, n)[rank * chunk:(rank + 1) * chunk])
+            else:
+                fn = lambda x_: shard_fn(tree, x_, n, gather=gather)
+            for i in range(2):
+                host_out.copy_(fn(host_chunks[i % NBUF].to(dev, non_blocking=True)), non_blocking=True)
+            barrier()
+            t0 = time.perf_counter()
+            for i in range(args.steps):
+                xd = host_chunks[i % NBUF].to(dev, non_blocking=True)
+                host_out.copy_(fn(xd), non_blocking=True)
+                torch.cuda.synchronize()
+            barrier()
+            return max_over_ranks((time.perf_counter() - t0) / args.steps)
+
+        e2e_s = e2e_loop(True)
+        extra["e2e_sharded_ms_per_step"] = e2e_loop(False) * 1e3
+        h2d, d2h = chunk * 32, n * 32
     clocks = sampler.stop()
 
+    products = products_per_elem(log_n) * n
+    whole_alg_gb = alg_bytes_per_elem(log_n) * n / 1e9
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -374,7 +422,7 @@ def main():
         "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3,
                 "path": ("ecfft_enter (host-buffer C ABI): pinned host coefficients -> H2D -> ENTER -> D2H -> pinned host evaluations" if world == 1
-                         else "per rank: pinned host chunk (n/N coefficients) -> H2D -> sharded ENTER -> D2H of this rank's n/N evaluations; bytes are per rank")},
+                         else "per rank: pinned host chunk (n/N coefficients) -> H2D -> sharded ENTER -> all-gather -> D2H of the WHOLE evaluation vector into every rank's pinned memory; bytes are per rank")},
         "gpu_launches": int(launches),
         "roofline": {
             "kernel": "k_extend_sym", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
@@ -382,45 +430,131 @@ def main():
             "peak_source": peak_src,
             "note": ("algorithmic bytes of the level-streaming model (SURVEY 8d); the kernel fuses ~10 levels and the combine "
                      "per HBM round trip, so achieved exceeds the physical peak while `traffic` (ncu DRAM bytes) is ~9x "
-                     "smaller: the kernel is bound by the integer multiplier, see integer_pipe"),
+                     "smaller: the kernel is bound by the integer multiplier, see integer_pipe_frac"),
             "kernel_ms_per_step": dom["ms_per_step"], "alg_gb_per_step": dom["alg_gb_per_step"],
             "launches_per_step": dom["launches_per_step"],
-            "whole_step": {"alg_gb": alg_bytes_per_elem(log_n) * n / 1e9,
-                           "achieved_gbs": alg_bytes_per_elem(log_n) * n / 1e9 / (ms_per_step * 1e-3),
-                           "frac": alg_bytes_per_elem(log_n) * n / 1e9 / (ms_per_step * 1e-3) / peak},
+            # flat scalars (nested objects do not survive the driver's parser)
+            "whole_step_alg_gb": whole_alg_gb,
+            "whole_step_achieved_gbs": whole_alg_gb / (ms_per_step * 1e-3),
+            "whole_step_frac": whole_alg_gb / (ms_per_step * 1e-3) / peak,
             "modmul_per_s_reference_count": modmuls_per_elem(log_n) * n / (ms_per_step * 1e-3),
             # what actually binds the kernel: the 32x32->64 integer multiplier
-            "integer_pipe": {
-                "products_per_step": products_per_elem(log_n) * n,
-                "products_per_s": products_per_elem(log_n) * n / (ms_per_step * 1e-3),
-                "frac_of_measured_product_peak": products_per_elem(log_n) * n / (ms_per_step * 1e-3) / PRODUCT_PEAK,
-                "peak_source": "tools/microbench.cu on B200: 108 G register-resident 256-bit products/s (IMAD.WIDE.X 9.1 T/s)",
-            },
-            "other_kernels": {"k_enter_combine": prof["k_enter_combine"]},
+            "integer_pipe_products_per_step": products,
+            "integer_pipe_products_per_s": products / (ms_per_step * 1e-3),
+            "integer_pipe_frac": products / (ms_per_step * 1e-3) / PRODUCT_PEAK / world,
+            "integer_pipe_peak_products_per_s_per_gpu": PRODUCT_PEAK,
+            "integer_pipe_peak_source": "tools/microbench.cu on B200: 108 G register-resident 256-bit products/s (IMAD.WIDE.X 9.1 T/s)",
+            "combine_kernel_ms_per_step": prof["k_enter_combine"]["ms_per_step"],
+            "combine_kernel_launches_per_step": prof["k_enter_combine"]["launches_per_step"],
         },
         "clocks": clocks,
     }
+    line.update(extra)
+
+    ok_all = True
+    if not args.no_configs:
+        cfg = run_configs(args, tree, world, rank, local_rank, dev, timed, all_ranks_true)
+        line.update(cfg)
+        ok_all = ok_all and all(v for k, v in cfg.items() if k.endswith("_matches_single") or k.endswith("_roundtrip_ok"))
+    if "multi_gpu_matches_single" in line:
+        ok_all = ok_all and line["multi_gpu_matches_single"]
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         s = cpu_sample(min(args.cpu_sample_log_n, log_n), log_n, threads=1)
         # the same sample on the GPU must agree bit for bit
         got = tree.enter(s["x"])
+        same = bool((got == s["out"]).all())
+        ok_all = ok_all and same
         line["cpu_baseline"] = {
             "value": s["evals_per_s"], "unit": UNIT, "cores": 1, "kind": "port",
             "sample": (f"oracle ENTER n=2^{min(args.cpu_sample_log_n, log_n)} single thread took {s['seconds']:.2f} s; scaled by "
                        f"field-multiplication count to n=2^{log_n} ({s['est_seconds_full']:.1f} s); GPU output on the sample "
-                       f"{'bit-identical' if (got == s['out']).all() else 'DIFFERS'}; host has {os.cpu_count()} logical cores"),
+                       f"{'bit-identical' if same else 'DIFFERS'}; host has {os.cpu_count()} logical cores"),
         }
         # and the last e2e result against nothing but itself run on device (same input): consistency of both paths
         chk = tree.enter(host_np[last_e2e_in])
         line["e2e"]["matches_device_path"] = bool((chk == out_np).all())
+        ok_all = ok_all and line["e2e"]["matches_device_path"]
+    line["self_check_ok"] = bool(ok_all)
     if rank == 0:
         print_json(line)
     if world > 1:
-        if args.multi_gpu == "peer":
+        if arena is not None:
             dist.barrier()          # nobody reads a peer arena any more
             arena.close()
         dist.destroy_process_group()
+    if not ok_all:
+        raise SystemExit("bench.py: a self-check failed (see *_matches_single / matches_device_path / cpu_baseline.sample)")
+
+
+def run_configs(args, tree22, world, rank, local_rank, dev, timed, all_ranks_true):
+    """The other BASELINE.json configurations as flat cfg_* keys (reference benches/fftree.rs:19-62 times the same
+    algorithms).  Device-resident buffers, CUDA events, median of 5 samples after 2 warm-ups."""
+    import numpy as np
+    import torch
+    import ecfft_b200
+    from oracle import oracle as O
+    from ecfft_b200.dist import PeerArena, enter_sharded_peer
+    out = {}
+
+    def median_ms(fn, warm=2, reps=5):
+        for _ in range(warm):
+            fn()
+        return statistics.median(timed(lambda i: fn(), 1) for _ in range(reps))
+
+    def to_dev(a):
+        return torch.from_numpy(a.view(np.int64)).to(dev)
+
+    if world == 1:
+        del tree22  # the headline tree carries only ENTER's tables; these configurations need the whole FFTree
+        t0 = time.perf_counter()
+        tree = ecfft_b200.build_fftree(1 << args.log_n, device=local_rank)
+        torch.cuda.synchronize()
+        out["cfg_full_tree_build_s"] = round(time.perf_counter() - t0, 3)
+        # configs[0]: ENTER -> EXIT round trip at n = 2^12
+        x12 = to_dev(O.random_elements(1 << 12, seed=11))
+        out["cfg_roundtrip_2p12_ms"] = median_ms(lambda: tree.exit(tree.enter(x12)))
+        out["cfg_roundtrip_2p12_roundtrip_ok"] = bool((tree.exit(tree.enter(x12)) == x12).all())
+        # configs[1]: EXTEND n = 2^20 (S0 -> S1 on the 2^21-leaf subtree)
+        x20 = to_dev(O.random_elements(1 << 20, seed=12))
+        ms = median_ms(lambda: tree.extend(x20, 1))
+        out["cfg_extend_2p20_ms"] = ms
+        out["cfg_extend_2p20_elems_per_s"] = (1 << 20) / (ms * 1e-3)
+        out["cfg_extend_2p20_roundtrip_ok"] = bool((tree.extend(tree.extend(x20, 1), 0) == x20).all())
+        # configs[4]: REDC + MOD n = 2^20 with matching-size tables (SURVEY 8d)
+        xnn = to_dev(tree.table("xnn_s", 1 << 20))
+        zz = to_dev(tree.table("z0z0_rem_xnn_s", 1 << 20))
+        out["cfg_redc_2p20_ms"] = median_ms(lambda: tree.redc_z0(x20, xnn))
+        out["cfg_mod_2p20_ms"] = median_ms(lambda: tree.modular_reduce(x20, xnn, zz))
+        # EXIT at the headline size (reference benches/fftree.rs:32-34) and EXIT(ENTER(x)) = x there
+        xn = to_dev(O.random_elements(1 << args.log_n, seed=13))
+        ev = tree.enter(xn)
+        ms = median_ms(lambda: tree.exit(ev), warm=1, reps=3)
+        out[f"cfg_exit_2p{args.log_n}_ms"] = ms
+        out[f"cfg_exit_2p{args.log_n}_elems_per_s"] = (1 << args.log_n) / (ms * 1e-3)
+        out[f"cfg_exit_2p{args.log_n}_roundtrip_ok"] = bool((tree.exit(ev) == xn).all())
+        return out
+
+    # N > 1 — configs[3]: ENTER n = 2^24 sharded over the N GPUs (peer schedule + final all-gather)
+    log_big = 24
+    nb = 1 << log_big
+    tree = ecfft_b200.build_fftree(nb, parts=ecfft_b200.PARTS_ENTER_ONLY, device=local_rank)
+    full = to_dev(O.random_elements(nb, seed=21))
+    c = nb // world
+    mine = full[rank * c:(rank + 1) * c].contiguous()
+    arena = PeerArena.create(nb, local_rank)
+    ms = median_ms(lambda: enter_sharded_peer(tree, mine, nb, arena), warm=2, reps=5)
+    out["cfg_2p24_ms"] = ms
+    out["cfg_2p24_evals_s"] = nb / (ms * 1e-3)
+    out["cfg_2p24_ms_without_final_allgather"] = median_ms(lambda: enter_sharded_peer(tree, mine, nb, arena, gather=False), warm=1, reps=5)
+    got = enter_sharded_peer(tree, mine, nb, arena)
+    want = tree.enter(full)
+    out["cfg_2p24_matches_single"] = all_ranks_true(bool((got == want).all()))
+    out["cfg_2p24_single_gpu_ms"] = median_ms(lambda: tree.enter(full), warm=1, reps=3)
+    import torch.distributed as dist
+    dist.barrier()
+    arena.close()
+    return out
 
 
 if __name__ == "__main__":

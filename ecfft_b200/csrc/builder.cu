@@ -81,6 +81,8 @@ static Tree* new_tree(size_t n, int parts, int device) {
   set_mempool_threshold(device);
   ECFFT_CUDA(cudaStreamCreateWithFlags(&t->stream, cudaStreamNonBlocking));
   t->f = t->dalloc(2 * n);
+  ECFFT_CUDA(cudaMalloc((void**)&t->build_errors, sizeof(unsigned long long)));
+  ECFFT_CUDA(cudaMemset(t->build_errors, 0, sizeof(unsigned long long)));
   return t;
 }
 
@@ -96,7 +98,7 @@ static void fill_internal_nodes(Tree& t) {
     ECFFT_CUDA(cudaMallocAsync((void**)&coeff, (cnt ? cnt : 1) * sizeof(Fp), st));
     if (!m.num.empty()) ECFFT_CUDA(cudaMemcpyAsync(coeff, m.num.data(), m.num.size() * sizeof(Fp), cudaMemcpyHostToDevice, st));
     if (!m.den.empty()) ECFFT_CUDA(cudaMemcpyAsync(coeff + m.num.size(), m.den.data(), m.den.size() * sizeof(Fp), cudaMemcpyHostToDevice, st));
-    k::ratmap_layer(t.f + (n >> (k + 1)), t.f + (n >> k), n >> (k + 1), coeff, (int)m.num.size(), coeff + m.num.size(), (int)m.den.size(), st);
+    k::ratmap_layer(t.f + (n >> (k + 1)), t.f + (n >> k), n >> (k + 1), coeff, (int)m.num.size(), coeff + m.num.size(), (int)m.den.size(), t.build_errors, st);
     ECFFT_CUDA(cudaStreamSynchronize(st));  // host coefficient vectors stay alive until the copy is done
     ECFFT_CUDA(cudaFreeAsync(coeff, st));
   }
@@ -168,7 +170,7 @@ void build_norm_tables(Tree& t, uint32_t k) {
     lv.gam[mu] = t.dalloc(hh);
     lv.gami[mu] = t.dalloc(hh);
     if (lv.sym) {
-      k::build_twiddles_sym(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, beta_dev, st);
+      k::build_twiddles_sym(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, beta_dev, t.build_errors, st);
       k::build_gamma_sym(lv.gam[mu], lv.rmat, t.f, stride, hh, mu, beta_dev, st);
     } else {
       k::build_twiddles(lv.tw_r[mu], lv.tw_d[mu], t.f, stride, hh, mu, st);
@@ -239,7 +241,7 @@ static void build_level(Tree& t, uint32_t k) {
     Fp* den = nullptr;
     ECFFT_CUDA(cudaMallocAsync((void**)&den, (m.den.size() ? m.den.size() : 1) * sizeof(Fp), st));
     if (!m.den.empty()) ECFFT_CUDA(cudaMemcpyAsync(den, m.den.data(), m.den.size() * sizeof(Fp), cudaMemcpyHostToDevice, st));
-    k::build_matrices(lv.rmat + 4 * d, lv.dmat + 4 * d, t.f + (n >> kk), stride, d, den, (int)m.den.size(), st);
+    k::build_matrices(lv.rmat + 4 * d, lv.dmat + 4 * d, t.f + (n >> kk), stride, d, den, (int)m.den.size(), t.build_errors, st);
     ECFFT_CUDA(cudaStreamSynchronize(st));
     ECFFT_CUDA(cudaFreeAsync(den, st));
   }
@@ -348,7 +350,11 @@ void finish_tree(Tree& t) {
     ECFFT_CUDA(cudaStreamSynchronize(t.stream));
   }
   for (uint32_t k = 0; k <= t.log_n; k++) build_level(t, k);
+  // the reference panics on these inputs (`unwrap()` at src/fftree.rs:57-58, :361); here they are an error code
+  unsigned long long bad = 0;
+  if (t.build_errors) ECFFT_CUDA(cudaMemcpyAsync(&bad, t.build_errors, sizeof bad, cudaMemcpyDeviceToHost, t.stream));
   ECFFT_CUDA(cudaStreamSynchronize(t.stream));
+  if (bad) throw Error(ERR_INVALID_ARG, "leaves / rational maps are degenerate: " + std::to_string(bad) + " zero denominators, singular matrices or nodes at a fixed point");
 }
 
 // Fp::build_fftree, reference src/lib.rs:39-85 (constants :45-59 in hex; tests check them against

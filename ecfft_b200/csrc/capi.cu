@@ -45,10 +45,11 @@ static cudaStream_t pick_stream(const ecfft_tree*, void* stream) { return (cudaS
 namespace {
 // scoped device buffer fed from / drained to host memory on the handle's stream
 struct HostIO {
+  DeviceGuard dev;
   const Tree& t;
   cudaStream_t st;
   std::vector<void*> bufs;
-  HostIO(const Tree& tree) : t(tree), st(tree.stream) { ECFFT_CUDA(cudaSetDevice(tree.device)); }
+  HostIO(const Tree& tree) : dev(tree.device), t(tree), st(tree.stream) {}
   ~HostIO() {
     for (void* b : bufs) cudaFreeAsync(b, st);
     cudaStreamSynchronize(st);
@@ -97,6 +98,10 @@ int ecfft_tree_build_secp256k1(size_t n, int parts, int device, ecfft_tree** out
   return guard([&] {
     require(out != nullptr, ERR_INVALID_ARG, "null out");
     require(parts == PARTS_FULL || parts == PARTS_ENTER_ONLY, ERR_INVALID_ARG, "bad parts");
+    // argument errors come before anything that needs a device (src/fftree.rs:44, src/lib.rs:61-64)
+    require(n && !(n & (n - 1)), ERR_NOT_POW2, "n is not a power of two");
+    require(n < ((size_t)1 << 36), ERR_TOO_LARGE, "FFTree size is too large for the generator (log2 n >= 36)");
+    DeviceGuard dev_guard(device);
     ecfft_tree* h = new ecfft_tree();
     try {
       h->tree = build_secp256k1(n, parts, device);
@@ -113,7 +118,8 @@ int ecfft_tree_new(const uint64_t* leaves, size_t n, const uint64_t* map_coeffs,
   return guard([&] {
     require(out && leaves && (nmaps == 0 || (map_coeffs && map_lens)), ERR_INVALID_ARG, "null argument");
     require(n && !(n & (n - 1)), ERR_NOT_POW2, "leaf count is not a power of two");
-    ECFFT_CUDA(cudaSetDevice(device));
+    require(parts == PARTS_FULL || parts == PARTS_ENTER_ONLY, ERR_INVALID_ARG, "bad parts");
+    DeviceGuard dev_guard(device);
     // Montgomery -> plain: leaves on the device, the few map coefficients on the host
     std::vector<RatMapHost> maps(nmaps);
     const Fp rinv = fp_const_RINV();
@@ -126,6 +132,7 @@ int ecfft_tree_new(const uint64_t* leaves, size_t n, const uint64_t* map_coeffs,
         for (size_t c = 0; c < cnt; c++) {
           Fp x;
           memcpy(&x, map_coeffs + 4 * (off + c), sizeof(Fp));
+          require(fp_eq(x, fp_canon(x)), ERR_INVALID_ARG, "rational-map coefficient is not a canonical field element");
           dst[c] = fp_mul(x, rinv);
         }
         off += cnt;
@@ -135,6 +142,19 @@ int ecfft_tree_new(const uint64_t* leaves, size_t n, const uint64_t* map_coeffs,
     ecfft_tree* h = new ecfft_tree();
     try {
       ECFFT_CUDA(cudaMemcpy(d, leaves, n * sizeof(Fp), cudaMemcpyHostToDevice));
+      {  // ark-ff elements are canonical (< p); anything else is not a field element
+        unsigned long long* cnt = nullptr;
+        unsigned long long bad = 0;
+        ECFFT_CUDA(cudaMalloc((void**)&cnt, sizeof bad));
+        cudaError_t e = cudaMemset(cnt, 0, sizeof bad);
+        if (e == cudaSuccess) {
+          k::count_noncanonical(cnt, d, n, nullptr);
+          e = cudaMemcpy(&bad, cnt, sizeof bad, cudaMemcpyDeviceToHost);
+        }
+        cudaFree(cnt);
+        ECFFT_CUDA(e);
+        require(bad == 0, ERR_INVALID_ARG, "leaves are not canonical field elements (limbs >= p)");
+      }
       k::mul_const(d, d, rinv, n, nullptr);
       ECFFT_CUDA(cudaDeviceSynchronize());
       h->tree = tree_from_leaves(d, n, maps, parts, device);
@@ -151,6 +171,7 @@ int ecfft_tree_new(const uint64_t* leaves, size_t n, const uint64_t* map_coeffs,
 int ecfft_tree_deserialize(const uint8_t* bytes, size_t len, int compressed, int device, ecfft_tree** out) {
   return guard([&] {
     require(out && bytes, ERR_INVALID_ARG, "null argument");
+    DeviceGuard dev_guard(device);
     ecfft_tree* h = new ecfft_tree();
     try {
       h->tree = deserialize(bytes, len, compressed != 0, device);
@@ -173,7 +194,7 @@ int ecfft_tree_serialize(const ecfft_tree* t, int compressed, uint8_t* buf, size
   return guard([&] {
     require(t && buf && written, ERR_INVALID_ARG, "null argument");
     std::lock_guard<std::mutex> lock(const_cast<ecfft_tree*>(t)->mu);
-    ECFFT_CUDA(cudaSetDevice(t->tree->device));
+    DeviceGuard dev_guard(t->tree->device);
     *written = serialize(*t->tree, compressed != 0, buf, cap);
   });
 }
@@ -366,7 +387,7 @@ int ecfft_vanish(const ecfft_tree* t, const uint64_t* vanish_domain, size_t n, u
 // ---- device-buffer algorithms -----------------------------------------------------------------
 #define DEV_ENGINE                                             \
   require(t != nullptr, ERR_INVALID_ARG, "null tree handle");  \
-  ECFFT_CUDA(cudaSetDevice(t->tree->device));                  \
+  DeviceGuard dev_guard(t->tree->device);                      \
   Engine eng(*t->tree, pick_stream(t, stream));
 
 int ecfft_enter_dev(const ecfft_tree* t, const void* d_coeffs, size_t n, void* d_evals, void* stream) {
@@ -472,7 +493,7 @@ int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* 
   return guard([&] {
     require(d_ptr && handle64 && bytes > 0, ERR_INVALID_ARG, "bad arena arguments");
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-    ECFFT_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
     void* p = nullptr;
     ECFFT_CUDA(cudaMalloc(&p, bytes));
     ECFFT_CUDA(cudaMemset(p, 0, bytes));
@@ -489,7 +510,7 @@ int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* 
 int ecfft_mg_arena_open(int device, const unsigned char* handle64, void** d_peer_ptr) {
   return guard([&] {
     require(d_peer_ptr && handle64, ERR_INVALID_ARG, "bad arena arguments");
-    ECFFT_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
     cudaIpcMemHandle_t h;
     memcpy(&h, handle64, 64);
     void* p = nullptr;
@@ -503,10 +524,16 @@ int ecfft_mg_arena_close(void* d_peer_ptr) {
 int ecfft_mg_arena_free(void* d_ptr) {
   return guard([&] { ECFFT_CUDA(cudaFree(d_ptr)); });
 }
+int ecfft_mg_arena_reset(void* d_ptr, void* stream) {
+  return guard([&] {
+    require(d_ptr != nullptr, ERR_INVALID_ARG, "null arena");
+    ECFFT_CUDA(cudaMemsetAsync(d_ptr, 0, MG_FLAG_BYTES, (cudaStream_t)stream));
+  });
+}
 int ecfft_selftest_field(int device, unsigned long long samples, unsigned long long* counters3) {
   return guard([&] {
     require(counters3 != nullptr, ERR_INVALID_ARG, "null output");
-    ECFFT_CUDA(cudaSetDevice(device));
+    DeviceGuard dev_guard(device);
     unsigned long long* d = nullptr;
     ECFFT_CUDA(cudaMalloc((void**)&d, 3 * sizeof(unsigned long long)));
     cudaError_t e = cudaMemset(d, 0, 3 * sizeof(unsigned long long));

@@ -17,10 +17,14 @@ static inline uint32_t ilog2(size_t n) {
 }
 
 Tree::~Tree() {
+  int prev = -1;
+  cudaGetDevice(&prev);
   cudaSetDevice(device);
+  if (build_errors) cudaFree(build_errors);
   for (void* p : owned) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
   for (cudaStream_t s : aux) cudaStreamDestroy(s);
+  if (prev >= 0 && prev != device) cudaSetDevice(prev);
 }
 Fp* Tree::dalloc(size_t count) {
   void* p = nullptr;

@@ -38,6 +38,36 @@ struct Error : std::runtime_error {
       throw ::ecfft::Error(::ecfft::ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
   } while (0)
 
+// Every entry point works on the tree's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != device) ECFFT_CUDA(cudaSetDevice(device));
+    else prev = -1;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+
+// cudaFuncSetAttribute is per device: a mutex-guarded bitmask of the devices a kernel has been configured on
+struct PerDeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0;
+  template <class F>
+  void run(F f) {
+    int d = 0;
+    ECFFT_CUDA(cudaGetDevice(&d));
+    std::lock_guard<std::mutex> lock(mu);
+    if (d < 64 && ((done >> d) & 1)) return;
+    f();
+    if (d < 64) done |= 1ull << d;
+  }
+};
+
 enum Moiety : int { S0 = 0, S1 = 1 };  // reference fftree.rs:17-21, declaration order
 // Whether the DATA flowing through an op is in Montgomery form (public API) or plain form
 // (tree construction).  Tables are always plain.  Only additive constants and
@@ -93,6 +123,7 @@ struct Tree {
   bool sym_ok = false;               // every map is (x^2 + c1 x + beta^2)/x
   int parts = PARTS_FULL;
   Fp base_leaf0, base_leaf1;         // leaves of the 2-leaf chain level (VANISH base case, fftree.rs:293-298)
+  unsigned long long* build_errors = nullptr;  // device counter: zero denominators / determinants / twiddles met while building
   cudaStream_t stream = nullptr;     // default stream for host-buffer calls
   std::vector<void*> owned;          // device allocations to free
   mutable std::vector<cudaStream_t> aux;  // helper streams ENTER forks independent ranges onto (engine.cu)
@@ -176,14 +207,15 @@ void sqr_sub_mul(Fp* out, const Fp* z_half, int z_parity, const Fp* xnn, const F
 void muladd(Fp* out, const Fp* a, const Fp* b, const Fp* c, size_t n, cudaStream_t st);  // out = a + b*c
 // tree construction
 void build_leaves(Fp* leaves, size_t n, Fp a, Fp a4, Fp offx, Fp offy, const Fp* gtab_xy /* log n points: 2^j * G */, uint32_t log_n, cudaStream_t st);
-void ratmap_layer(Fp* layer, const Fp* prev, size_t count, const Fp* num, int nnum, const Fp* den, int nden, cudaStream_t st);
-void build_matrices(Fp* rmat_layer, Fp* dmat_layer, const Fp* flayer, size_t fstride, size_t d, const Fp* den, int nden, cudaStream_t st);
+// err (may be null): device counter of the inputs the reference would panic on (zero denominator, singular matrix)
+void ratmap_layer(Fp* layer, const Fp* prev, size_t count, const Fp* num, int nnum, const Fp* den, int nden, unsigned long long* err, cudaStream_t st);
+void build_matrices(Fp* rmat_layer, Fp* dmat_layer, const Fp* flayer, size_t fstride, size_t d, const Fp* den, int nden, unsigned long long* err, cudaStream_t st);
 // normalised tables of one chain level (h = N/2 entries each); f_top strided by fstride is the level's f
 void build_twiddles(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
 void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st);
 void fold_sumform_prescale(Fp* gami, const Fp* f_top, size_t fstride, size_t h, int mu, cudaStream_t st);
 // symmetric-form tables; beta_by_j[j] is the fixed point of the map used by the level with half-stride 2^j
-void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st);
+void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, unsigned long long* err, cudaStream_t st);
 void build_gamma_sym(Fp* gam, const Fp* rmat, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st);
 void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st);
 void selftest_field(unsigned long long* counters3, unsigned long long samples, cudaStream_t st);  // device self-test of the lazy add/sub forms  // out[i] = a[i]*b[b_off + i*b_stride]
@@ -227,6 +259,7 @@ struct Engine {
 static constexpr size_t MG_FLAG_BYTES = 4096;
 static constexpr unsigned MG_DONE_FLAG = MG_FLAG_BYTES / 8 - 1;  // "this rank has finished call `epoch`"
 size_t peer_arena_bytes(size_t n, int world);
+unsigned peer_timeout_ms();  // ECFFT_B200_PEER_TIMEOUT_MS (default 20000, 0 = wait for ever)
 void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int world, void* const* bases,
                 unsigned long long epoch, Fp* out_chunk);
 

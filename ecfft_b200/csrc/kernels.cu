@@ -369,16 +369,19 @@ __device__ __forceinline__ Fp poly_eval_dev(const Fp* c, int n, const Fp& x) {
   return acc;
 }
 // layer[i] = num(prev[i]) / den(prev[i])   (RationalMap::map, reference src/utils.rs:383-385)
-void ratmap_layer(Fp* layer, const Fp* prev, size_t count, const Fp* num, int nnum, const Fp* den, int nden, cudaStream_t st) {
+// A zero denominator (the reference's `rational_map.map(..).unwrap()` panics, src/fftree.rs:57-58) is counted in *err.
+void ratmap_layer(Fp* layer, const Fp* prev, size_t count, const Fp* num, int nnum, const Fp* den, int nden, unsigned long long* err, cudaStream_t st) {
   map(count, st, [=] __device__(size_t i) {
     Fp x = fp_load(prev + i);
     Fp nu = poly_eval_dev(num, nnum, x), de = poly_eval_dev(den, nden, x);
+    if (err && fp_is_zero(de)) atomicAdd(err, 1ull);
     fp_store(layer + i, fp_mul(nu, fp_inv(de)));
   });
 }
 // Lemma 3.2 matrices of one layer, reference src/fftree.rs:354-362.  flayer has 2d entries at
 // stride fstride (the chain level's f layer is a strided view of the top tree's).
-void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, const Fp* den, int nden, cudaStream_t st) {
+// A singular matrix (the reference's `rmat.inverse().unwrap()` panics, src/fftree.rs:361) is counted in *err.
+void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, const Fp* den, int nden, unsigned long long* err, cudaStream_t st) {
   uint64_t e = d / 2 - 1;
   map(d, st, [=] __device__(size_t i) {
     Fp s0 = fp_load(flayer + i * fstride), s1 = fp_load(flayer + (i + d) * fstride);
@@ -386,6 +389,7 @@ void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, 
     Fp v1 = fp_pow_u64(poly_eval_dev(den, nden, s1), e);
     Fp r0 = v0, r1 = fp_mul(s0, v0), r2 = v1, r3 = fp_mul(s1, v1);
     Fp det = fp_sub(fp_mul(r0, r3), fp_mul(r1, r2));
+    if (err && fp_is_zero(det)) atomicAdd(err, 1ull);
     Fp di = fp_inv(det);
     Fp* r = rl + 4 * i;
     Fp* m = dl + 4 * i;
@@ -455,7 +459,7 @@ __global__ void k_mg_sync(unsigned long long* own_flag, unsigned long long value
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w[i]) : "memory");
       if (v >= value) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > timeout_ns) __trap();
+      if (timeout_ns && t - t0 > timeout_ns) __trap();  // 0 = wait for ever
       __nanosleep(100);
     }
   }
@@ -472,7 +476,7 @@ __global__ void k_mg_wait_all(ArenaBases b, int world, int rank, unsigned idx, u
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(b.base[r] + idx) : "memory");
       if (v >= value) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (t - t0 > timeout_ns) __trap();
+      if (timeout_ns && t - t0 > timeout_ns) __trap();  // 0 = wait for ever
       __nanosleep(100);
     }
   }
@@ -558,7 +562,7 @@ void build_gamma(Fp* gam, const Fp* rmat, size_t h, int mu, cudaStream_t st) {
 // Symmetric-form tables (DESIGN.md 4.1 "symmetric"): the level's map x -> (x^2 + c1 x + beta^2)/x
 // identifies s with beta^2/s, and g(s) = (s - beta)/(s + beta) takes opposite values on the two.
 // Entry idx = 2^j + i holds g(s0) resp. 1/g(s0) for s0 = the pair's lower node.
-void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, cudaStream_t st) {
+void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, size_t h, int mu, const Fp* beta_by_j, unsigned long long* err, cudaStream_t st) {
   map(h, st, [=] __device__(size_t idx) {
     if (idx == 0) {
       fp_store(tw_r, fp_zero());
@@ -570,6 +574,7 @@ void build_twiddles_sym(Fp* tw_r, Fp* tw_d, const Fp* f_top, size_t fstride, siz
     Fp s0 = fp_load(f_top + (2 * B + 2 * i + mu) * fstride);
     Fp b = fp_load_ro(beta_by_j + j);
     Fp nu = fp_sub(s0, b), de = fp_add(s0, b);
+    if (err && (fp_is_zero(nu) || fp_is_zero(de))) atomicAdd(err, 1ull);  // a node at a fixed point +-beta of the involution
     Fp t = fp_inv(fp_mul(nu, de));
     fp_store(tw_r + idx, fp_mul(fp_mul(nu, nu), t));
     fp_store(tw_d + idx, fp_mul(fp_mul(de, de), t));

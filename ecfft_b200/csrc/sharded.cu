@@ -13,6 +13,8 @@
 // stream-ordered u64 flags (k::mg_sync).  A call starts by waiting until every peer has finished the previous
 // call (its reads of this rank's arena included) and ends by publishing that itself has — a device-side
 // barrier.  No host round trip, no send/recv, no collective.
+#include <cstdlib>
+
 #include "engine.h"
 
 namespace ecfft {
@@ -21,6 +23,19 @@ static inline uint32_t ilog2(size_t n) {
   uint32_t l = 0;
   while (n >>= 1) l++;
   return l;
+}
+
+// How long a flag wait may last before the waiting kernel traps (a CUDA error on the next call rather than a
+// hung GPU): ECFFT_B200_PEER_TIMEOUT_MS, default 20000, 0 = wait for ever (ranks that may reach a call far
+// apart in time — a tree build or data loading on one of them — should raise it or use 0).
+unsigned peer_timeout_ms() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_PEER_TIMEOUT_MS");
+    long t = e ? atol(e) : 20000;
+    v = t < 0 ? 20000 : (t > 0x7fffffff ? 0x7fffffff : (int)t);
+  }
+  return (unsigned)v;
 }
 
 static size_t peer_slots(int world) {
@@ -47,7 +62,7 @@ void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int worl
     eng.enter_range(chunk, out_chunk, n, 1, n);
     return;
   }
-  const unsigned timeout_ms = 20000;
+  const unsigned timeout_ms = peer_timeout_ms();
   size_t next_slot = 0, sid = 0;
   auto slot = [&](int r, size_t idx, size_t off = 0) { return (Fp*)((char*)bases[r] + MG_FLAG_BYTES) + idx * c + off; };
   auto flag = [&](int r, size_t s) { return (unsigned long long*)bases[r] + s; };

@@ -287,11 +287,8 @@ static uint32_t sym_log_tile() { return sym_variant() == 3 ? 11 : sym_variant() 
 
 template <int NT, int MINB>
 static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp))));
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  configured.run([] { ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp)))); });
   k_extend_sym<NT, MINB><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
 }
 

@@ -188,11 +188,8 @@ static uint32_t log_tile() { return tile_variant() == 1 ? 11 : 10; }
 
 template <int MODE, int NT, int MINB, bool SOA>
 static void launch_variant(const TileParams& p, size_t tiles, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<MODE, NT, MINB, SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp))));
-    configured = true;
-  }
+  static PerDeviceOnce configured;
+  configured.run([] { ECFFT_CUDA(cudaFuncSetAttribute(k_extend_tile<MODE, NT, MINB, SOA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp)))); });
   k_extend_tile<MODE, NT, MINB, SOA><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
 }
 template <int MODE>

@@ -159,8 +159,10 @@ class FFTree:
         import torch
         x0 = tensors[0]
         for x in tensors:
-            if x.device.index != self.device or x.dtype not in (torch.int64, torch.uint64) or x.dim() != 2 or x.shape[1] != 4:
+            if not _is_torch_cuda(x) or x.device.index != self.device or x.dtype not in (torch.int64, torch.uint64) or x.dim() != 2 or x.shape[1] != 4:
                 raise EcfftError(_lib.ERR_INVALID_ARG, "expected (n,4) int64/uint64 CUDA tensors on the tree's device")
+            if x.shape[0] != x0.shape[0]:   # the C entry points take ONE n: a shorter operand would be read out of bounds
+                raise EcfftError(_lib.ERR_INVALID_ARG, "operand lengths differ")
         tensors = [x.contiguous() for x in tensors]
         out = torch.empty((out_rows, 4), dtype=x0.dtype, device=x0.device)
         stream = torch.cuda.current_stream(x0.device).cuda_stream
@@ -203,7 +205,10 @@ class FFTree:
         d = ctypes.c_size_t()
         if _is_torch_cuda(evals):
             import torch
-            x = evals.contiguous()
+            x = evals
+            if x.device.index != self.device or x.dtype not in (torch.int64, torch.uint64) or x.dim() != 2 or x.shape[1] != 4:
+                raise EcfftError(_lib.ERR_INVALID_ARG, "expected an (n,4) int64/uint64 CUDA tensor on the tree's device")
+            x = x.contiguous()
             stream = torch.cuda.current_stream(x.device).cuda_stream
             _lib.check(self._L.ecfft_degree_dev(self._h, ctypes.c_void_p(x.data_ptr()), x.shape[0], ctypes.byref(d), ctypes.c_void_p(stream)))
         else:

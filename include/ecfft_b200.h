@@ -130,12 +130,18 @@ int ecfft_mg_combine_dev(const ecfft_tree* t, size_t m, size_t i0, const void* d
  *   arena_alloc : zeroed device memory on `device` plus its 64-byte IPC handle (to be sent to the peers)
  *   arena_open  : map a peer's arena into this process (peer access enabled lazily); arena_close unmaps
  *   signal/wait : stream-ordered u64 flags inside arenas (release / acquire at system scope).  A wait not
- *                 satisfied within timeout_ms traps (a CUDA error on the next call, never a hung GPU). */
+ *                 satisfied within timeout_ms traps (a CUDA error on the next call, never a hung GPU);
+ *                 timeout_ms = 0 waits for ever.  ecfft_enter_peer_dev takes its timeout from the environment
+ *                 variable ECFFT_B200_PEER_TIMEOUT_MS (default 20000, 0 = for ever): raise it when ranks can
+ *                 reach a call far apart in time (a tree build or data loading on one of them).
+ *   arena_reset : after an aborted call (an error on one rank leaves flags and epochs out of step) every rank
+ *                 zeroes the flags of its OWN arena, the ranks meet at a host barrier, and epochs restart at 1. */
 int ecfft_mg_arena_bytes(size_t n, int world, size_t* bytes);   /* arena size ecfft_enter_peer_dev needs */
 int ecfft_mg_arena_alloc(int device, size_t bytes, void** d_ptr, unsigned char* handle64);
 int ecfft_mg_arena_open(int device, const unsigned char* handle64, void** d_peer_ptr);
 int ecfft_mg_arena_close(void* d_peer_ptr);
 int ecfft_mg_arena_free(void* d_ptr);
+int ecfft_mg_arena_reset(void* d_ptr, void* stream);
 int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream);
 int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned timeout_ms, void* stream);
 /* The whole per-rank schedule of the sharded ENTER in one call (reference src/fftree.rs:143-161 for the

@@ -188,6 +188,13 @@ static void batch_inversion_fast(fe* v, size_t n) {
   free(prod);
 }
 
+/* Thread budget of the tree BUILD (orc_set_build_threads; default 1 = the reference's single thread).  The
+ * loops it cuts into ranges are element-wise, so the tables are bit-identical for any budget; it only
+ * shortens the set-up of the CPU baseline at n = 2^22 (bench.py --impl reference). */
+static int g_build_threads = 1;
+void orc_set_build_threads(int threads) { g_build_threads = threads < 1 ? 1 : threads; }
+static void parallel_for(size_t n, int threads, void (*fn)(size_t, size_t, void*), void* ctx);
+
 void orc_fe_mul(const fe* a, const fe* b, fe* r) { fe_mul(r, a, b); }
 void orc_fe_add(const fe* a, const fe* b, fe* r) { fe_add(r, a, b); }
 void orc_fe_sub(const fe* a, const fe* b, fe* r) { fe_sub(r, a, b); }
@@ -861,6 +868,66 @@ int orc_vanish(const orc_tree* t, const fe* domain, size_t n, fe* out) {
 /* ------------------------------------------------------------------------- */
 static orc_tree* from_tree(fe* f, size_t n, const ratmap* maps, size_t nmaps, int parts);
 
+/* element-wise loops of from_tree / fftree_new as ranges (see g_build_threads) */
+typedef struct { const fe* s; fe *xnnnn, *xnn; uint64_t nnnn, nn; } pow_ctx;
+static void pow_range(size_t lo, size_t hi, void* p) {  /* fftree.rs:328-331 */
+  pow_ctx* c = (pow_ctx*)p;
+  for (size_t i = lo; i < hi; i++) {
+    fe_pow(&c->xnnnn[i], &c->s[i], c->nnnn);
+    fe_pow(&c->xnn[i], &c->s[i], c->nn);
+  }
+}
+typedef struct { const fe* l; size_t d; const ratmap* map; fe *rl, *dl, *det; } mat_ctx;
+static void mat_r_range(size_t lo, size_t hi, void* p) {  /* fftree.rs:354-360 */
+  mat_ctx* c = (mat_ctx*)p;
+  const size_t d = c->d;
+  for (size_t i = lo; i < hi; i++) {
+    fe s0 = c->l[i], s1 = c->l[i + d], v0, v1;
+    poly_eval(&v0, c->map->den, c->map->nden, &s0);
+    poly_eval(&v1, c->map->den, c->map->nden, &s1);
+    fe_pow(&v0, &v0, d / 2 - 1);
+    fe_pow(&v1, &v1, d / 2 - 1);
+    fe* r = c->rl + 4 * i;
+    r[0] = v0;
+    fe_mul(&r[1], &s0, &v0);
+    r[2] = v1;
+    fe_mul(&r[3], &s1, &v1);
+    /* Mat2x2::inverse, utils.rs:325-335: one determinant inverse per matrix (batched by the caller) */
+    fe a, b;
+    fe_mul(&a, &r[0], &r[3]);
+    fe_mul(&b, &r[1], &r[2]);
+    fe_sub(&c->det[i], &a, &b);
+  }
+}
+static void mat_d_range(size_t lo, size_t hi, void* p) {  /* fftree.rs:361 */
+  mat_ctx* c = (mat_ctx*)p;
+  for (size_t i = lo; i < hi; i++) {
+    const fe* r = c->rl + 4 * i;
+    fe* m = c->dl + 4 * i;
+    fe neg;
+    fe_mul(&m[0], &r[3], &c->det[i]);
+    fe_neg(&neg, &r[1]);
+    fe_mul(&m[1], &neg, &c->det[i]);
+    fe_neg(&neg, &r[2]);
+    fe_mul(&m[2], &neg, &c->det[i]);
+    fe_mul(&m[3], &r[0], &c->det[i]);
+  }
+}
+typedef struct { const point* offset; const point* gen; fe* leaves; } leaf_ctx;
+static void leaf_range(size_t lo, size_t hi, void* p) {  /* lib.rs:72-78 from acc = lo * gen */
+  leaf_ctx* c = (leaf_ctx*)p;
+  point acc = point_zero(), g = *c->gen;
+  for (size_t e = lo; e; e >>= 1) {  /* lo * gen by double-and-add: the group law gives the same point */
+    if (e & 1) acc = point_add(&acc, &g);
+    g = point_add(&g, &g);
+  }
+  for (size_t i = lo; i < hi; i++) {
+    point q = point_add(c->offset, &acc);
+    c->leaves[i] = q.x;
+    acc = point_add(&acc, c->gen);
+  }
+}
+
 /* fftree.rs:465-482 */
 static orc_tree* derive_subtree(const fe* f, size_t n_parent, const ratmap* maps, size_t nmaps, int parts) {
   size_t n = n_parent / 2;
@@ -892,9 +959,9 @@ static orc_tree* from_tree(fe* f, size_t n, const ratmap* maps, size_t nmaps, in
   fe* xnnnn_s_inv = fe_alloc(n);
   t->xnn_s = fe_alloc(n);
   t->xnn_s_inv = fe_alloc(n);
-  for (size_t i = 0; i < n; i++) {
-    fe_pow(&xnnnn_s[i], &s[i], nnnn);
-    fe_pow(&t->xnn_s[i], &s[i], nn);
+  {
+    pow_ctx pc = {s, xnnnn_s, t->xnn_s, nnnn, nn};
+    parallel_for(n, g_build_threads, pow_range, &pc);
   }
   memcpy(xnnnn_s_inv, xnnnn_s, n * sizeof(fe));
   batch_inversion_fast(xnnnn_s_inv, n);
@@ -916,35 +983,10 @@ static orc_tree* from_tree(fe* f, size_t n, const ratmap* maps, size_t nmaps, in
     fe* rl = t->rmat + 4 * d;    /* matrix layer k, size d, at offset d */
     fe* dl = t->dmat + 4 * d;
     fe* det = fe_alloc(d);
-    for (size_t i = 0; i < d; i++) {
-      fe s0 = l[i], s1 = l[i + d], v0, v1;
-      poly_eval(&v0, maps[k].den, maps[k].nden, &s0);
-      poly_eval(&v1, maps[k].den, maps[k].nden, &s1);
-      fe_pow(&v0, &v0, d / 2 - 1);
-      fe_pow(&v1, &v1, d / 2 - 1);
-      fe* r = rl + 4 * i;
-      r[0] = v0;
-      fe_mul(&r[1], &s0, &v0);
-      r[2] = v1;
-      fe_mul(&r[3], &s1, &v1);
-      /* Mat2x2::inverse, utils.rs:325-335: one determinant inverse per matrix (batched here) */
-      fe a, b;
-      fe_mul(&a, &r[0], &r[3]);
-      fe_mul(&b, &r[1], &r[2]);
-      fe_sub(&det[i], &a, &b);
-    }
+    mat_ctx mc = {l, d, &maps[k], rl, dl, det};
+    parallel_for(d, g_build_threads, mat_r_range, &mc);
     batch_inversion_fast(det, d);
-    for (size_t i = 0; i < d; i++) {
-      const fe* r = rl + 4 * i;
-      fe* m = dl + 4 * i;
-      fe neg;
-      fe_mul(&m[0], &r[3], &det[i]);
-      fe_neg(&neg, &r[1]);
-      fe_mul(&m[1], &neg, &det[i]);
-      fe_neg(&neg, &r[2]);
-      fe_mul(&m[2], &neg, &det[i]);
-      fe_mul(&m[3], &r[0], &det[i]);
-    }
+    parallel_for(d, g_build_threads, mat_d_range, &mc);
     free(det);
   }
 
@@ -1087,11 +1129,9 @@ orc_tree* orc_build_fftree(size_t n, int parts) {
   for (unsigned i = 0; i < two_adicity_of_generator - log_n; i++) gen = point_add(&gen, &gen);
 
   fe* leaves = fe_alloc(n);
-  point acc = point_zero();
-  for (size_t i = 0; i < n; i++) {
-    point q = point_add(&offset, &acc);
-    leaves[i] = q.x;
-    acc = point_add(&acc, &gen);
+  {
+    leaf_ctx lc = {&offset, &gen, leaves};
+    parallel_for(n, g_build_threads, leaf_range, &lc);
   }
   /* find_isogeny_chain, ec.rs:177-189 */
   int k = two_adicity(gen);

@@ -47,6 +47,8 @@ void orc_batch_inversion(fe* v, size_t n);
  * parts: 0 = full tree (reference behaviour); 1 = only what ENTER/EXTEND(S1)
  * touch (f, matrices, xnn_s, xnn_s_inv) — used for the large CPU-baseline trees. */
 orc_tree* orc_build_fftree(size_t n, int parts);
+/* threads the element-wise loops of the tree build may use (default 1); tables are identical for any value */
+void orc_set_build_threads(int threads);
 void orc_tree_free(orc_tree* t);
 size_t orc_tree_leaves(const orc_tree* t);
 const orc_tree* orc_subtree_with_size(const orc_tree* t, size_t n); /* src/fftree.rs:489-496; NULL if too small */

@@ -39,6 +39,8 @@ def lib():
         L.orc_build_fftree.restype = vp
         L.orc_build_fftree.argtypes = [sz, ci]
         L.orc_tree_free.argtypes = [vp]
+        L.orc_set_build_threads.argtypes = [ci]
+        L.orc_set_build_threads.restype = None
         L.orc_tree_leaves.restype = sz
         L.orc_tree_leaves.argtypes = [vp]
         L.orc_subtree_with_size.restype = vp
@@ -110,8 +112,13 @@ class OracleTree:
         self._owner = owner
 
     @classmethod
-    def build(cls, n, parts=0):
-        h = lib().orc_build_fftree(n, parts)
+    def build(cls, n, parts=0, threads=1):
+        """threads > 1 only shortens the build (element-wise loops cut into ranges); the tables are identical"""
+        lib().orc_set_build_threads(threads)
+        try:
+            h = lib().orc_build_fftree(n, parts)
+        finally:
+            lib().orc_set_build_threads(1)
         if not h:
             raise OracleError("build_fftree returned None")
         return cls(h)

@@ -315,6 +315,86 @@ def test_full_size_extend_redc_mod(tree22, oracle_mod):
     assert tree22.degree(h) < n // 2
 
 
+# ---- oracle-exact checks at sizes that take the multi-outer-pass path of the EXTEND kernel (log_h >= 16) ----
+def test_large_oracle_exact_enter_2p18(tree22, oracle_mod):
+    """ENTER n = 2^18 bit for bit against the oracle (its top depths run EXTENDs of 2^16 and 2^17 elements: two
+    outer strided passes + the inner pass + the fused combine pass)."""
+    import os
+    n = 1 << 18
+    cpu = oracle_mod.OracleTree.build(n, parts=1, threads=os.cpu_count() or 1)
+    x = oracle_mod.random_elements(n, seed=218)
+    eq(tree22.enter(x), cpu.enter(x, threads=os.cpu_count() or 1))
+
+
+def test_large_oracle_exact_exit_extend_redc_2p17(tree22, oracle_mod):
+    """EXIT, EXTEND (both moieties), REDC and MOD at n = 2^17 bit for bit against the oracle (full tables)."""
+    import os
+    n = 1 << 17
+    cpu = oracle_mod.OracleTree.build(n, threads=os.cpu_count() or 1)
+    x = oracle_mod.random_elements(n, seed=217)
+    ev = cpu.enter(x, threads=os.cpu_count() or 1)
+    eq(tree22.enter(x), ev)
+    eq(tree22.exit(ev), x)
+    y = oracle_mod.random_elements(n, seed=2170)
+    eq(tree22.exit(y), cpu.exit(y))                  # evaluations of no low-degree polynomial in particular
+    half = oracle_mod.random_elements(n // 2, seed=2171)
+    for moiety in (0, 1):
+        eq(tree22.subtree_with_size(n).extend(half, moiety), cpu.extend(half, moiety))
+    a = cpu.table("xnn_s")
+    c = cpu.table("z0z0_rem_xnn_s")
+    eq(tree22.redc_z0(y, a), cpu.redc_z0(y, a))
+    eq(tree22.modular_reduce(y, a, c), cpu.modular_reduce(y, a, c))
+
+
+def test_device_calls_reject_operands_of_different_length(trees, oracle_mod):
+    """redc / modular_reduce with a shorter `a` or `c` CUDA tensor must be refused (the C entry points take
+    ONE n), and degree() validates its tensor like the other calls."""
+    import torch
+    import ecfft_b200
+    gpu, _ = trees
+    n = 1024
+    x = torch.from_numpy(oracle_mod.random_elements(n, seed=5).view(np.int64)).cuda()
+    short = x[: n // 2].contiguous()
+    for call in (lambda: gpu.redc_z0(x, short), lambda: gpu.redc_z1(x, short),
+                 lambda: gpu.modular_reduce(x, x, short), lambda: gpu.modular_reduce(x, short, x)):
+        with pytest.raises(ecfft_b200.EcfftError) as e:
+            call()
+        assert e.value.code == ecfft_b200._lib.ERR_INVALID_ARG
+    with pytest.raises(ecfft_b200.EcfftError):
+        gpu.degree(x.to(torch.int32))
+    with pytest.raises(ecfft_b200.EcfftError):
+        gpu.degree(x[:, :2])
+
+
+def test_tree_new_rejects_degenerate_and_noncanonical_input(trees, oracle_mod):
+    """FFTree::new panics in the reference on a zero denominator / singular matrix (unwrap at src/fftree.rs:57-58,
+    :361); here the build fails with ERR_INVALID_ARG, and so do limbs >= p."""
+    import ecfft_b200
+    from oracle import pyref
+    n = 16
+    leaves = oracle_mod.OracleTree.build(n).leaves().copy()
+    zero = np.zeros(4, dtype=np.uint64)
+    p = pyref.P
+    a, bb = pyref.A, pyref.BB
+    maps = []
+    for _ in range(4):                               # r = (x^2 - 2b x + b^2) / x  (src/ec.rs:84)
+        b = pow(bb, (p + 1) // 4, p)
+        maps.append((oracle_mod.to_mont([bb, (-2 * b) % p, 1]), oracle_mod.to_mont([0, 1])))
+        a, bb = (a + 6 * b) % p, (4 * a * b + 8 * b * b) % p
+    ok = ecfft_b200.FFTree.new(leaves, maps)
+    assert ok.leaves_count == n
+    bad = leaves.copy()
+    bad[3] = zero                                    # x = 0 is the pole of every map (x - b)^2 / x
+    with pytest.raises(ecfft_b200.EcfftError) as e:
+        ecfft_b200.FFTree.new(bad, maps)
+    assert e.value.code == ecfft_b200._lib.ERR_INVALID_ARG
+    big = leaves.copy()
+    big[0] = np.array([0xFFFFFFFFFFFFFFFF] * 4, dtype=np.uint64)   # >= p
+    with pytest.raises(ecfft_b200.EcfftError) as e:
+        ecfft_b200.FFTree.new(big, maps)
+    assert e.value.code == ecfft_b200._lib.ERR_INVALID_ARG
+
+
 def test_host_buffer_enter_pipeline_equals_device_path(tree22, oracle_mod):
     """ecfft_enter uploads three chunks on a copy stream and runs the low recursion depths on each while the
     next is in flight; every element must equal the single device-resident ENTER
