@@ -34,7 +34,7 @@ SYMBOLS = [
     "ecfft_mg_prescale_dev", "ecfft_mg_cross_dev", "ecfft_mg_local_dev", "ecfft_mg_combine_dev",
     "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free", "ecfft_mg_arena_reset",
     "ecfft_mg_signal_dev", "ecfft_mg_wait_dev", "ecfft_mg_arena_bytes", "ecfft_enter_peer_dev",
-    "ecfft_selftest_field",
+    "ecfft_selftest_field", "ecfft_flow_stats",
 ]
 
 
@@ -107,6 +107,7 @@ def load():
     L.ecfft_enter_peer_dev.argtypes = [vp, vp, sz, ci, ci, pvp, ctypes.c_ulonglong, vp, vp]
     L.ecfft_mg_signal_dev.argtypes = [vp, ctypes.c_ulonglong, vp]
     L.ecfft_mg_wait_dev.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_uint, vp]
+    L.ecfft_flow_stats.argtypes = [ci, ctypes.POINTER(ctypes.c_ulonglong)]
     L.ecfft_launch_count.restype = ctypes.c_ulonglong
     L.ecfft_launch_count.argtypes = []
     L.ecfft_profile_enable.restype = None

@@ -87,6 +87,13 @@ int ecfft_profile_read(int kernel, double* ms, double* alg_bytes, unsigned long 
   });
 }
 
+int ecfft_flow_stats(int enable, unsigned long long* out4) {
+  return guard([&] {
+    if (out4) k::flow_stats_read(out4);
+    k::flow_stats_enable(enable != 0);
+  });
+}
+
 int ecfft_device_count(int* count) {
   return guard([&] {
     require(count != nullptr, ERR_INVALID_ARG, "null count");

@@ -109,6 +109,7 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
   }
+  if (enter_range_flow(in, out, n, m_lo, m_hi)) return;
   // Independent ranges on concurrent streams: range s runs the depths up to m_mid (the largest block size
   // that tiles a range) on stream s, the caller's stream joins them and runs the remaining depths.
   const int S = enter_streams();
@@ -137,6 +138,58 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
     }
   }
   enter_range_serial(in, out, n, m_lo, m_hi);
+}
+
+// All depths m_lo < m <= m_hi as ONE flow launch (sym_kernel.cu: persistent CTAs, per-block dependency counters
+// instead of kernel boundaries).  The work buffers alternate by depth parity: everything a depth reads or
+// writes lies inside its own aligned m-block, and a tile of depth d+1 only starts once the depth-d results of
+// its whole block are complete, so a buffer is never overwritten while a tile still needs its old contents.
+bool Engine::enter_range_flow(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
+  if (!k::flow_enabled() || k::butterfly_mode() != 2) return false;
+  const size_t T = (size_t)1 << k::flow_log_tile();
+  if (n % T || m_lo == m_hi) return false;
+  for (size_t m = m_lo * 2; m <= m_hi; m *= 2) {
+    const Level& lv = level_for(m);
+    if (!(lv.sym && lv.has_norm())) return false;
+  }
+  Fp* W[2] = {nullptr, nullptr};
+  Fp* ping[2] = {nullptr, nullptr};
+  k::SymFlow flow;
+  const Fp* cur = in;
+  uint32_t idx = 0;
+  for (size_t m = m_lo * 2; m <= m_hi; m *= 2, idx++) {
+    const Level& lv = level_for(m);
+    const size_t h = m / 2;
+    const uint32_t log_h = ilog2(h);
+    Fp* dst;
+    if (m == m_hi && out != in) {
+      dst = out;
+    } else {
+      if (!ping[idx & 1]) ping[idx & 1] = tmp(n);
+      dst = ping[idx & 1];
+    }
+    k::SymCombine c{cur, lv.xnn_s, lv.gam[1], lv.gx, dst};
+    if (h == 1) {
+      k::plan_combine_only(flow, c, cur, 0, n);   // EXTEND of a length-1 vector is the identity (fftree.rs:74-76)
+    } else {
+      if (log_h + 1 > k::flow_log_tile() && !W[idx & 1]) W[idx & 1] = tmp(n);
+      Fp* Wd = W[idx & 1];
+      if (!k::plan_extend_sym(flow, lv.tw_d[0], lv.tw_r[1], lv.ctr[1], cur, Wd, log_h, n / h, lv.gami[0], nullptr, &c)) {
+        // a vector fills the tile: EXTEND (unscaled) into the work buffer, then the combine as its own pass
+        if (!k::plan_extend_sym(flow, lv.tw_d[0], lv.tw_r[1], lv.ctr[1], cur, Wd, log_h, n / h, lv.gami[0], nullptr, nullptr))
+          throw Error(ERR_INVALID_ARG, "enter: EXTEND refused a depth it should take");
+        k::plan_combine_only(flow, c, Wd, log_h, n);
+      }
+    }
+    cur = dst;
+  }
+  k::launch_flow(flow, st);
+  if (cur != out) ECFFT_CUDA(cudaMemcpyAsync(out, cur, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+  release(W[0]);
+  release(W[1]);
+  release(ping[0]);
+  release(ping[1]);
+  return true;
 }
 
 void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {

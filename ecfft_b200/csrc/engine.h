@@ -162,6 +162,58 @@ void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaSt
 // unscaled input, and the result goes to comb->out.  Returns false when it does not apply (fewer than 4
 // elements; a depth whose vector length equals the tile cannot take the fused combine).
 struct SymCombine { const Fp* A; const Fp* xnn; const Fp* gam; const Fp* gx; Fp* out; };
+// One pass of k_extend_sym (a launch of the per-pass kernel, or one entry of a flow: sym_kernel.cu)
+struct SymParams {
+  const Fp* in;
+  Fp* out;
+  const Fp* tw_d;   // 1/g of the source moiety, entry 2^j + i
+  const Fp* tw_r;   // g of the target moiety
+  const Fp* ctr;    // one element: g_target / g_source at level 0 (the centre of the network)
+  const Fp* pre;    // per-position scale applied by the first stage (or null)
+  const Fp* post;   // per-position scale applied by the last stage (or null); ignored when comb != 0
+  const Fp* A;      // combine epilogue: the unscaled input vectors [u0 | v0] per block
+  const Fp* xnn;
+  const Fp* gam;
+  const Fp* gx;
+  unsigned long long nv;      // strided: vectors (pair: vector pairs) in the batch; blocks are ordered batch-major
+  unsigned long long total;   // elements in the batch (guards the ragged tile of tiny inputs)
+  uint32_t log_h, log_t;
+  uint32_t lvl_lo, lvl_hi;    // this pass runs the levels lvl_lo <= j < lvl_hi
+  uint32_t boff;              // tile-index bit of level j is j + boff (mod 2^32)
+  uint32_t packed;            // 1: tile = 2^log_t consecutive elements (whole vectors, or a slice of one: inner pass)
+  uint32_t log_c, krows, row_shift;  // strided: 2^krows rows of 2^log_c contiguous elements, rows 2^row_shift apart
+  uint32_t pair;              // strided: top tile bit selects vector 2w / 2w+1
+  uint32_t comb;              // 1: combine epilogue
+  uint32_t do_d, do_r;
+  // strided views (REDC's de-interleave / interleave, src/fftree.rs:234, 258): logical element g of the
+  // batch is read at in[(g << in_shift) + in_off] by the first pass and written at out[(g << out_shift) +
+  // out_off] by the last; E/Z: the last pass stores E[(g << e_shift) + e_off] * Z[i] + x * post[i]
+  uint32_t in_shift, in_off, out_shift, out_off, e_shift, e_off;
+  const Fp* E;
+  const Fp* Z;
+  // ---- flow fields (k_sym_flow: all passes of an ENTER in one persistent launch) ----
+  uint32_t kind;              // 0: butterfly tile pass; 1: combine-only pass (in = [u1 | v1] unscaled, A = [u0 | v0])
+  uint32_t tile_begin, ntiles;         // this pass's range of the flow's tile queue
+  uint32_t ord_tpb_log, ord_nv, ord_log_v;  // queue order within the pass: (block, vector, tile in block), see finalize_flow
+  uint32_t dep_base, dep_shift, dep_need;   // wait until counter[dep_base + (first input element >> dep_shift)] >= dep_need (0: none)
+  uint32_t sig_base, sig_shift;             // then add 1 to counter[sig_base + (first output element >> sig_shift)]
+};
+// A flow: passes whose tiles depend only on an aligned block of the previous pass's output (butterfly networks
+// and ENTER's combine are block-local), executed by ONE launch of persistent CTAs that take tiles from a queue
+// in dependency order and wait on per-block completion counters instead of kernel boundaries.
+struct SymFlow {
+  std::vector<SymParams> passes;
+  double alg_bytes = 0;   // level-streaming model, summed (bench roofline)
+};
+// appends the passes of one symmetric EXTEND (same arguments as extend_sym) / one combine-only pass; false: not applicable
+bool plan_extend_sym(SymFlow& flow, const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
+                     const Fp* pre, const Fp* post, const SymCombine* comb, const struct SymIO* io = nullptr);
+void plan_combine_only(SymFlow& flow, const SymCombine& c, const Fp* W, uint32_t log_h, size_t n);
+bool flow_enabled();            // ECFFT_B200_FLOW (default 1)
+uint32_t flow_log_tile();
+void launch_flow(SymFlow& flow, cudaStream_t st);   // throws if the flow does not fit one launch
+void flow_stats_enable(bool on);                     // diagnostics: per-launch wait / body / signal cycles of the flow CTAs
+void flow_stats_read(unsigned long long out4[4]);    // {wait cycles, body cycles, signal cycles, tiles}; clears
 // Strided views for REDC (fftree.rs:232-259): logical element g is read at in[(g << in_shift) + in_off] and
 // written at out[(g << out_shift) + out_off]; with E the store is E[(g << e_shift) + e_off] * Z[i] + x * post[i]
 // (i = position within the vector).  work: contiguous scratch of nvec * h elements for multi-pass EXTENDs.
@@ -242,6 +294,7 @@ struct Engine {
   // the FFTree<F> surface (fftree.rs:72-316) on device buffers
   void enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // bottom-up levels m_lo < m <= m_hi
   void enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // ... on this engine's stream only
+  bool enter_range_flow(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;    // ... as one flow launch (false: not applicable)
   void enter(const Fp* coeffs, Fp* out, size_t n) const { enter_range(coeffs, out, n, 1, n); }
   void exit(const Fp* evals, Fp* out, size_t n) const;
   bool exit_depths(Fp* cur, Fp* nxt, Fp* M, size_t len, size_t m_from, size_t m_stop) const;

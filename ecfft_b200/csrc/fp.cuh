@@ -633,6 +633,15 @@ FP_D Fp fp_load_ro(const Fp* p) {
   r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
   return r;
 }
+// L2-only load: data another CTA of the same launch may have written (never served from L1)
+FP_D Fp fp_load_cg(const Fp* p) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+  uint4 a = __ldcg(q), b = __ldcg(q + 1);
+  Fp r;
+  r.v[0] = a.x; r.v[1] = a.y; r.v[2] = a.z; r.v[3] = a.w;
+  r.v[4] = b.x; r.v[5] = b.y; r.v[6] = b.z; r.v[7] = b.w;
+  return r;
+}
 FP_D void fp_store(Fp* p, const Fp& x) {
   uint4* q = reinterpret_cast<uint4*>(p);
   q[0] = make_uint4(x.v[0], x.v[1], x.v[2], x.v[3]);

@@ -26,36 +26,6 @@
 namespace ecfft {
 namespace k {
 
-struct SymParams {
-  const Fp* in;
-  Fp* out;
-  const Fp* tw_d;   // 1/g of the source moiety, entry 2^j + i
-  const Fp* tw_r;   // g of the target moiety
-  const Fp* ctr;    // one element: g_target / g_source at level 0 (the centre of the network)
-  const Fp* pre;    // per-position scale applied by the first stage (or null)
-  const Fp* post;   // per-position scale applied by the last stage (or null); ignored when comb != 0
-  const Fp* A;      // combine epilogue: the unscaled input vectors [u0 | v0] per block
-  const Fp* xnn;
-  const Fp* gam;
-  const Fp* gx;
-  unsigned long long nv;      // strided: vectors (pair: vector pairs) in the batch; blocks are ordered batch-major
-  unsigned long long total;   // elements in the batch (guards the ragged tile of tiny inputs)
-  uint32_t log_h, log_t;
-  uint32_t lvl_lo, lvl_hi;    // this pass runs the levels lvl_lo <= j < lvl_hi
-  uint32_t boff;              // tile-index bit of level j is j + boff (mod 2^32)
-  uint32_t packed;            // 1: tile = 2^log_t consecutive elements (whole vectors, or a slice of one: inner pass)
-  uint32_t log_c, krows, row_shift;  // strided: 2^krows rows of 2^log_c contiguous elements, rows 2^row_shift apart
-  uint32_t pair;              // strided: top tile bit selects vector 2w / 2w+1
-  uint32_t comb;              // 1: combine epilogue
-  uint32_t do_d, do_r;
-  // strided views (REDC's de-interleave / interleave, src/fftree.rs:234, 258): logical element g of the
-  // batch is read at in[(g << in_shift) + in_off] by the first pass and written at out[(g << out_shift) +
-  // out_off] by the last; E/Z: the last pass stores E[(g << e_shift) + e_off] * Z[i] + x * post[i]
-  uint32_t in_shift, in_off, out_shift, out_off, e_shift, e_off;
-  const Fp* E;
-  const Fp* Z;
-};
-
 enum : uint32_t { OP_D_HI = 1, OP_D_LO = 2, OP_R_LO = 4, OP_R_HI = 8, OP_C_LO = 16 };
 
 struct TileSoA {
@@ -108,9 +78,12 @@ struct TileMap {
   }
 };
 
-template <int NT, int MINB>
-__global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__ SymParams p) {
-  extern __shared__ uint4 smem_raw[];
+// One tile of one pass.  Packed tiles start at element gbase_packed; strided tiles are tile `tile` of vector
+// (pair) w.  FLOW: the data buffers may have been written by other CTAs of the SAME launch, so every read of
+// them goes to L2 (cp.async.cg, ld.global.cg), never through L1.
+template <int NT, bool FLOW>
+__device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, unsigned long long w, unsigned long long tile,
+                                         unsigned long long gbase_packed) {
   const uint32_t T = 1u << p.log_t;
   const TileSoA s{smem_raw, T};
   const uint32_t hmask = (1u << p.log_h) - 1;
@@ -118,10 +91,8 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
   unsigned long long gbase;
   if (p.packed) {
     tm = TileMap{p.log_t, T - 1, 0u, 0u, 0u, p.log_h, 0u};
-    gbase = (unsigned long long)blockIdx.x << p.log_t;
+    gbase = gbase_packed;
   } else {
-    const unsigned long long w = blockIdx.x % p.nv;
-    const unsigned long long tile = blockIdx.x / p.nv;
     const uint32_t ncg_log = p.row_shift - p.log_c;
     const uint32_t cg = (uint32_t)(tile & ((1ull << ncg_log) - 1));
     const uint32_t q_hi = (uint32_t)(tile >> ncg_log);
@@ -240,7 +211,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
       const uint32_t i = pos & hmask;
       Fp x = s.ld(e);
       if (p.E)
-        x = fp_dot2_lazy(fp_load(p.E + ((g << p.e_shift) + p.e_off)), fp_load_ro(p.Z + i), x, fp_load_ro(p.post + i));
+        x = fp_dot2_lazy(FLOW ? fp_load_cg(p.E + ((g << p.e_shift) + p.e_off)) : fp_load(p.E + ((g << p.e_shift) + p.e_off)), fp_load_ro(p.Z + i), x, fp_load_ro(p.post + i));
       else if (p.post)
         x = fp_mul_lazy(x, fp_load_ro(p.post + i));
       fp_store(p.out + ((g << p.out_shift) + p.out_off), fp_canon(x));
@@ -263,11 +234,141 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
       if (gv >= p.total) continue;
       const uint32_t i = pu & hmask;
       Fp* o = p.out + (gu - i) + 2ull * i;
-      const Fp u0 = fp_load(p.A + gu), v0 = fp_load(p.A + gv);
+      const Fp u0 = FLOW ? fp_load_cg(p.A + gu) : fp_load(p.A + gu), v0 = FLOW ? fp_load_cg(p.A + gv) : fp_load(p.A + gv);
       fp_store(o, fp_canon(fp_muladd_lazy(u0, v0, fp_load_ro(p.xnn + 2 * i))));
       const Fp u1 = s.ld(eu), v1 = s.ld(ev);
       fp_store(o + 1, fp_canon(fp_dot2_lazy(fp_load_ro(p.gam + i), u1, fp_load_ro(p.gx + i), v1)));
     }
+  }
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__ SymParams p) {
+  extern __shared__ uint4 smem_raw[];
+  if (p.packed)
+    sym_tile<NT, false>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t);
+  else
+    sym_tile<NT, false>(p, smem_raw, blockIdx.x % p.nv, blockIdx.x / p.nv, 0);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Flow kernel: every pass of an ENTER (all recursion depths: EXTEND passes, fused and plain combines) in ONE
+// launch.  Persistent CTAs (one per resident slot) take tiles from a global queue; the queue lists the passes
+// in order and, inside a pass, the tiles in the order their inputs become ready.  A tile waits until the
+// aligned block of the previous pass's output it reads is complete (a counter per block, release/acquire at
+// GPU scope) — butterfly levels and the combine only ever read inside such a block, so no kernel boundary
+// and no grid-wide barrier is needed, and the tail of one pass overlaps the head of the next.
+// Deadlock freedom: a tile only waits for tiles with smaller queue numbers, which were taken earlier by CTAs
+// that are running (only running CTAs take tiles).
+// ------------------------------------------------------------------------------------------------------
+static constexpr int FLOW_MAX_PASSES = 112;
+struct FlowDesc {
+  SymParams pass[FLOW_MAX_PASSES];
+  uint32_t npass, total_tiles;
+  unsigned int* queue;      // next tile number
+  unsigned int* counters;   // per (pass, block) completed-tile counts
+  unsigned long long* stats;  // null, or 4 diagnostic accumulators (ecfft_flow_stats)
+};
+static_assert(sizeof(FlowDesc) <= 32764, "flow descriptor must fit the kernel parameter space");
+
+__device__ __forceinline__ unsigned ld_acquire_gpu(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu(unsigned* p, unsigned v) {
+  asm volatile("fence.acq_rel.gpu;\n\tred.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_sym_flow(const __grid_constant__ FlowDesc d) {
+  extern __shared__ uint4 smem_raw[];
+  __shared__ unsigned s_next[2];
+  __shared__ unsigned* s_prev_sig;                     // counter of the tile this CTA finished last (signalled late)
+  __shared__ long long s_acc[4];                       // diagnostics: wait, body, signal cycles, tiles
+  uint32_t k = 0, it = 0;
+  if (threadIdx.x == 0) {
+    s_next[0] = atomicAdd(d.queue, 1u);
+    s_acc[0] = s_acc[1] = s_acc[3] = 0;
+  }
+  if (threadIdx.x == NT - 1) {
+    s_prev_sig = nullptr;
+    s_acc[2] = 0;
+  }
+  for (;; it++) {
+    __syncthreads();                                   // s_next[it & 1] is there; every store of the previous tile has been issued
+    const unsigned g = s_next[it & 1];
+    if (threadIdx.x == NT - 1 && s_prev_sig) {         // the previous tile's results are complete: publish (release, GPU scope)
+      const long long t0 = d.stats ? clock64() : 0;
+      red_release_gpu(s_prev_sig, 1u);
+      if (d.stats) s_acc[2] += clock64() - t0;
+    }
+    if (g >= d.total_tiles) break;
+    if (threadIdx.x == 0) s_next[(it + 1) & 1] = atomicAdd(d.queue, 1u);   // the next tile's number arrives while this one runs
+    while (g >= d.pass[k].tile_begin + d.pass[k].ntiles) k++;
+    const SymParams& p = d.pass[k];
+    // queue position inside the pass -> (block b, vector w, tile i of the block) -> tile t_v of vector w
+    const uint32_t sq = g - p.tile_begin;
+    const uint32_t i = sq & ((1u << p.ord_tpb_log) - 1), t1 = sq >> p.ord_tpb_log;
+    const uint32_t w = t1 % p.ord_nv, b = t1 / p.ord_nv;
+    const unsigned long long t_v = ((unsigned long long)b << p.ord_tpb_log) | i;
+    unsigned long long first_in, first_out, gbase_packed = 0;
+    if (p.kind == 1 || p.packed) {
+      gbase_packed = ((unsigned long long)w << p.ord_log_v) + (t_v << p.log_t);
+      first_in = first_out = gbase_packed;
+    } else {
+      const uint32_t ncg_log = p.row_shift - p.log_c;
+      const unsigned long long pos0 = ((t_v >> ncg_log) << p.lvl_hi) + ((t_v & ((1ull << ncg_log) - 1)) << p.log_c);
+      first_in = ((unsigned long long)(p.pair ? 2 * w : w) << p.log_h) + pos0;
+      first_out = p.pair ? ((unsigned long long)w << (p.log_h + 1)) + 2 * pos0 : first_in;
+    }
+    if (threadIdx.x == NT - 1) s_prev_sig = d.counters + p.sig_base + (unsigned)(first_out >> p.sig_shift);
+    if (p.dep_need) {
+      if (threadIdx.x == 0) {
+        const long long t0 = d.stats ? clock64() : 0;
+        const unsigned* c = d.counters + p.dep_base + (unsigned)(first_in >> p.dep_shift);
+        if (ld_acquire_gpu(c) < p.dep_need) {
+          // a dependency that never completes would be a bug in the plan: trap (a CUDA error) rather than hang the GPU
+          unsigned long long ta, tb;
+          asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ta));
+          unsigned ns = 64;
+          while (ld_acquire_gpu(c) < p.dep_need) {
+            __nanosleep(ns);                            // back off: many waiting CTAs poll the same few counters
+            if (ns < 1024) ns *= 2;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tb));
+            if (tb - ta > 10000000000ull) __trap();
+          }
+        }
+        if (d.stats) s_acc[0] += clock64() - t0;
+      }
+      __syncthreads();
+    }
+    if (d.stats && threadIdx.x == 0) s_acc[1] -= clock64();
+    if (p.kind == 0) {
+      sym_tile<NT, true>(p, smem_raw, w, t_v, gbase_packed);
+    } else {
+      // combine-only pass (src/fftree.rs:155-159): outputs [first_out, first_out + T) of the batch
+      const uint32_t T = 1u << p.log_t;
+      const unsigned long long pair0 = gbase_packed >> 1, hm = (1ull << p.log_h) - 1;
+#pragma unroll 1
+      for (uint32_t e = threadIdx.x; e < T / 2; e += NT) {
+        const unsigned long long idx = pair0 + e, blk = idx >> p.log_h, ii = idx & hm, off = blk << (p.log_h + 1);
+        if (off + (1ull << p.log_h) + ii >= p.total) continue;
+        const Fp u0 = fp_load_cg(p.A + off + ii), v0 = fp_load_cg(p.A + off + (1ull << p.log_h) + ii);
+        fp_store(p.out + off + 2 * ii, fp_canon(fp_muladd_lazy(u0, v0, fp_load_ro(p.xnn + 2 * ii))));
+        const Fp u1 = fp_load_cg(p.in + off + ii), v1 = fp_load_cg(p.in + off + (1ull << p.log_h) + ii);
+        fp_store(p.out + off + 2 * ii + 1, fp_canon(fp_dot2_lazy(fp_load_ro(p.gam + ii), u1, fp_load_ro(p.gx + ii), v1)));
+      }
+    }
+    if (d.stats && threadIdx.x == 0) { s_acc[1] += clock64(); s_acc[3]++; }
+  }
+  if (d.stats) {   // diagnostics (ecfft_flow_stats): cycles thread 0 spent waiting for inputs / in tile bodies, signal cycles
+    if (threadIdx.x == 0) {
+      atomicAdd(d.stats + 0, (unsigned long long)s_acc[0]);
+      atomicAdd(d.stats + 1, (unsigned long long)s_acc[1]);
+      atomicAdd(d.stats + 3, (unsigned long long)s_acc[3]);
+    }
+    if (threadIdx.x == NT - 1) atomicAdd(d.stats + 2, (unsigned long long)s_acc[2]);
   }
 }
 
@@ -284,6 +385,20 @@ static int sym_variant() {
   return v;
 }
 static uint32_t sym_log_tile() { return sym_variant() == 3 ? 11 : sym_variant() == 4 ? 9 : 10; }
+uint32_t flow_log_tile() { return sym_log_tile(); }
+bool flow_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // Off by default: measured on B200 (profiles/r02_c_*, r02_d_*) the flow launch is 4-10 % slower than one
+    // launch per pass at every size — its tile body runs from a dynamically indexed pass table (no
+    // constant-bank operands: 96 registers with spills, or 126 registers at 4 CTAs/SM) and the per-tile
+    // queue / counter traffic costs ~2.5 %, while the drains it removes are already filled by the
+    // two-stream ENTER.
+    const char* e = getenv("ECFFT_B200_FLOW");
+    v = e ? (atoi(e) != 0) : 0;
+  }
+  return v != 0;
+}
 
 template <int NT, int MINB>
 static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
@@ -292,18 +407,21 @@ static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
   k_extend_sym<NT, MINB><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
 }
 
+// algorithmic bytes (level-streaming model of the reference algorithm): every level reads and writes each
+// element once (64 B) and reads its 2^j matrices (128 B) once; a combine moves 128 B per element
+static double pass_alg_bytes(const SymParams& p) {
+  if (p.kind == 1) return 128.0 * (double)p.total;
+  const double levels = (double)(p.lvl_hi - p.lvl_lo) * (p.do_d + p.do_r);
+  double mats = 0;
+  for (uint32_t j = p.lvl_lo; j < p.lvl_hi; j++) mats += (double)(p.do_d + p.do_r) * 128.0 * (double)(1ull << j);
+  return levels * 64.0 * (double)p.total + mats + (p.comb ? 128.0 * (double)p.total : 0.0);
+}
+
 static void launch_sym(const SymParams& p, cudaStream_t st) {
   const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
   if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
   const bool timed = prof::enabled();
-  if (timed) {
-    // algorithmic bytes (level-streaming model of the reference algorithm): every level reads and writes
-    // each element once (64 B) and reads its 2^j matrices (128 B) once; a combine moves 128 B per element
-    const double levels = (double)(p.lvl_hi - p.lvl_lo) * (p.do_d + p.do_r);
-    double mats = 0;
-    for (uint32_t j = p.lvl_lo; j < p.lvl_hi; j++) mats += (double)(p.do_d + p.do_r) * 128.0 * (double)(1ull << j);
-    prof::record_begin(prof::EXTEND_TILE, levels * 64.0 * (double)p.total + mats + (p.comb ? 128.0 * (double)p.total : 0.0), st);
-  }
+  if (timed) prof::record_begin(prof::EXTEND_TILE, pass_alg_bytes(p), st);
   switch (sym_variant()) {
     case 1: launch_shape<128, 4>(p, tiles, st); break;
     case 2: launch_shape<256, 3>(p, tiles, st); break;
@@ -316,11 +434,12 @@ static void launch_sym(const SymParams& p, cudaStream_t st) {
   ECFFT_CUDA(cudaGetLastError());
 }
 
-// All passes of the symmetric EXTEND of nvec vectors of length 2^log_h.  comb != null fuses ENTER's combine
-// into the last pass (nvec even: vectors 2w, 2w+1 are u, v of block w); returns false when this depth
-// cannot be fused (the caller then runs EXTEND and the combine kernel separately).
-bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
-                const SymCombine* comb, cudaStream_t st, const SymIO* io) {
+// All passes of the symmetric EXTEND of nvec vectors of length 2^log_h, appended to flow.passes.  comb != null
+// fuses ENTER's combine into the last pass (nvec even: vectors 2w, 2w+1 are u, v of block w); returns false
+// when this depth cannot be fused (the caller then runs EXTEND and the combine separately).
+bool plan_extend_sym(SymFlow& flow, const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
+                     const Fp* pre, const Fp* post, const SymCombine* comb, const SymIO* io) {
+  std::vector<SymParams>& L = flow.passes;
   const uint32_t LT = sym_log_tile();
   const size_t total = nvec << log_h;
   if (total < 4 || log_h == 0 || log_h > 31) return false;
@@ -369,7 +488,7 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
     p.nv = 1;
     set_first(p);
     set_last(p);
-    launch_sym(p, st);
+    L.push_back(p);
     return true;
   }
   if (io && !mid) throw Error(ERR_INVALID_ARG, "extend_sym: multi-pass EXTEND with strided views needs a work buffer");
@@ -393,7 +512,7 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
     p.do_d = 1; p.do_r = 0;
     p.pre = i == 0 ? pre : nullptr;
     p.post = nullptr;
-    launch_sym(p, st);
+    L.push_back(p);
     src = mid;
   }
   // inner pass: all levels below the tile size on contiguous tiles
@@ -403,7 +522,7 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
   p.lvl_lo = 0; p.lvl_hi = LT; p.boff = 0; p.do_d = 1; p.do_r = 1;
   p.pre = npass == 0 ? pre : nullptr;
   p.post = npass == 0 ? post : nullptr;
-  launch_sym(p, st);
+  L.push_back(p);
   for (uint32_t i = npass; i-- > 0;) {              // outer recombine passes, top levels last
     const bool fin = i == 0;
     p.in = mid; p.out = (fin && comb) ? comb->out : (fin ? out : mid);
@@ -417,9 +536,189 @@ bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp*
     p.do_d = 0; p.do_r = 1;
     p.pre = nullptr;
     p.post = (fin && !comb) ? post : nullptr;
-    launch_sym(p, st);
+    L.push_back(p);
   }
   return true;
+}
+
+// One launch per pass (the per-pass kernel).  Same result as running the planned passes as a flow.
+bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
+                const SymCombine* comb, cudaStream_t st, const SymIO* io) {
+  SymFlow flow;
+  if (!plan_extend_sym(flow, tw_d, tw_r, ctr, in, out, log_h, nvec, pre, post, comb, io)) return false;
+  for (const SymParams& p : flow.passes) launch_sym(p, st);
+  return true;
+}
+
+// ENTER's combine as a pass of its own (depths whose EXTEND cannot carry it: h = 1, where EXTEND is the
+// identity, and h = tile).  W = [u1 | v1] per block, unscaled (gam / gx carry Gamma^1).
+void plan_combine_only(SymFlow& flow, const SymCombine& c, const Fp* W, uint32_t log_h, size_t n) {
+  SymParams p{};
+  p.kind = 1;
+  p.in = W;
+  p.out = c.out;
+  p.A = c.A;
+  p.xnn = c.xnn;
+  p.gam = c.gam;
+  p.gx = c.gx;
+  p.total = n;
+  p.log_h = log_h;
+  p.log_t = sym_log_tile();
+  p.nv = 1;
+  flow.passes.push_back(p);
+}
+
+static int flow_order() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_FLOW_ORDER");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+static unsigned long long* g_flow_stats = nullptr;   // device buffer of 4 accumulators when diagnostics are on
+void flow_stats_enable(bool on) {
+  if (on && !g_flow_stats) {
+    ECFFT_CUDA(cudaMalloc((void**)&g_flow_stats, 4 * sizeof(unsigned long long)));
+    ECFFT_CUDA(cudaMemset(g_flow_stats, 0, 4 * sizeof(unsigned long long)));
+  } else if (!on && g_flow_stats) {
+    cudaFree(g_flow_stats);
+    g_flow_stats = nullptr;
+  }
+}
+void flow_stats_read(unsigned long long out4[4]) {
+  if (!g_flow_stats) throw Error(ERR_INVALID_ARG, "flow statistics are not enabled");
+  ECFFT_CUDA(cudaDeviceSynchronize());
+  ECFFT_CUDA(cudaMemcpy(out4, g_flow_stats, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  ECFFT_CUDA(cudaMemset(g_flow_stats, 0, 4 * sizeof(unsigned long long)));
+}
+static inline uint32_t umax(uint32_t a, uint32_t b) { return a > b ? a : b; }
+static inline uint32_t umin(uint32_t a, uint32_t b) { return a < b ? a : b; }
+
+// Queue order, dependencies and counters of a flow.  Pass k reads, per tile, inside ONE aligned block of
+// 2^Din elements of its input and writes inside one aligned block of 2^Dout elements of its output:
+//   packed tile      Din = Dout = log_t            (whole vectors or a slice of one)
+//   strided tile     Din = Dout = lvl_hi           (rows 2^lvl_lo apart span a 2^lvl_hi block of the vector)
+//   pair tile        Din = Dout = log_h + 1        (u and v are neighbours; the outputs interleave over the block)
+//   combine-only     Din = Dout = max(log_t, log_h + 1)
+// The counters of pass k have the granularity G_k = max(Dout_k, Din_{k+1}); a tile of pass k+1 waits for the
+// one counter covering its input block to reach the number of tiles of pass k in such a block.  Inside a
+// pass the queue runs block-major over the PREVIOUS pass's counters — (block, vector, tile in block) — so
+// tiles are taken in the order their inputs complete.  Returns the number of counters.
+static uint32_t finalize_flow(std::vector<SymParams>& P) {
+  const size_t K = P.size();
+  std::vector<uint32_t> Din(K), Dout(K), G(K);
+  for (size_t k = 0; k < K; k++) {
+    const SymParams& p = P[k];
+    if (p.total % ((size_t)1 << p.log_t)) throw Error(ERR_INVALID_ARG, "flow: a pass does not tile evenly");
+    uint32_t dd;
+    if (p.kind == 1) dd = umax(p.log_t, p.log_h + 1);
+    else if (p.packed) dd = p.log_t;
+    else if (p.pair) dd = p.log_h + 1;
+    else dd = p.lvl_hi;
+    Din[k] = Dout[k] = dd;
+  }
+  uint32_t ncounters = 0, tiles = 0;
+  for (size_t k = 0; k < K; k++) {
+    SymParams& p = P[k];
+    G[k] = k + 1 < K ? umax(Dout[k], Din[k + 1]) : Dout[k];
+    if (p.total % ((size_t)1 << G[k])) throw Error(ERR_INVALID_ARG, "flow: a pass does not split into whole dependency blocks");
+    p.sig_base = ncounters;
+    p.sig_shift = G[k];
+    ncounters += (uint32_t)(p.total >> G[k]);
+    p.ntiles = (uint32_t)(p.total >> p.log_t);
+    p.tile_begin = tiles;
+    tiles += p.ntiles;
+    if (k == 0) {
+      p.dep_need = 0;
+      p.dep_base = p.dep_shift = 0;
+    } else {
+      p.dep_base = P[k - 1].sig_base;
+      p.dep_shift = G[k - 1];
+      p.dep_need = 1u << (G[k - 1] - P[k - 1].log_t);
+    }
+    // order
+    const uint32_t gin = k == 0 ? Din[0] : G[k - 1];
+    uint32_t tv_log;  // log2 tiles per ordering vector
+    if (p.kind == 1 || (p.packed && p.log_h <= p.log_t)) {
+      p.ord_nv = 1; p.ord_log_v = 0; tv_log = 0;      // natural order over the whole batch
+      p.ord_tpb_log = 0;
+    } else {
+      const uint32_t log_v = p.pair ? p.log_h + 1 : p.log_h;
+      const size_t nv = p.total >> log_v;
+      if (nv == 0 || nv > 0xffffffffull) throw Error(ERR_INVALID_ARG, "flow: bad batch");
+      p.ord_nv = (uint32_t)nv;
+      p.ord_log_v = log_v;
+      tv_log = log_v - p.log_t;
+      // vector-major (natural) order by default: a pair's two vectors then complete together, half-way
+      // through a pass, and a tile's producers sit about one whole pass earlier in the queue.
+      // ECFFT_B200_FLOW_ORDER=1: block-major over the previous pass's counters (measured slower).
+      p.ord_tpb_log = flow_order() == 1 ? (gin > p.log_t ? umin(gin - p.log_t, tv_log) : 0) : tv_log;
+    }
+  }
+  return ncounters;
+}
+
+template <int NT, int MINB>
+static void launch_flow_shape(const FlowDesc& d, uint32_t log_t, uint32_t widest_pass, cudaStream_t st) {
+  static PerDeviceOnce configured;
+  static int slots_per_sm[64];
+  int dev = 0;
+  ECFFT_CUDA(cudaGetDevice(&dev));
+  const size_t smem = ((size_t)sizeof(Fp)) << log_t;
+  configured.run([&] {
+    ECFFT_CUDA(cudaFuncSetAttribute(k_sym_flow<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp))));
+    int nb = 0, sms = 0;
+    ECFFT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_sym_flow<NT, MINB>, NT, smem));
+    ECFFT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    if (dev < 64) slots_per_sm[dev] = (nb > 0 ? nb : 1) * sms;
+  });
+  unsigned grid = dev < 64 && slots_per_sm[dev] > 0 ? (unsigned)slots_per_sm[dev] : 148u * MINB;
+  // no more CTAs than the widest pass has tiles: the others could only take tiles of later passes and spin
+  if (grid > widest_pass) grid = widest_pass;
+  if (grid > d.total_tiles) grid = d.total_tiles;
+  k_sym_flow<NT, MINB><<<grid, NT, smem, st>>>(d);
+}
+
+void launch_flow(SymFlow& flow, cudaStream_t st) {
+  if (flow.passes.empty()) return;
+  if (flow.passes.size() > (size_t)FLOW_MAX_PASSES) throw Error(ERR_INVALID_ARG, "flow: too many passes");
+  const uint32_t ncounters = finalize_flow(flow.passes);
+  FlowDesc d{};
+  uint32_t log_t = 0, widest = 1;
+  double bytes = 0;
+  for (size_t k = 0; k < flow.passes.size(); k++) {
+    d.pass[k] = flow.passes[k];
+    log_t = umax(log_t, flow.passes[k].log_t);
+    widest = umax(widest, flow.passes[k].ntiles);
+    bytes += pass_alg_bytes(flow.passes[k]);
+  }
+  flow.alg_bytes = bytes;
+  d.npass = (uint32_t)flow.passes.size();
+  const SymParams& last = flow.passes.back();
+  const unsigned long long tt = (unsigned long long)last.tile_begin + last.ntiles;
+  if (tt > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "flow: too many tiles");
+  d.total_tiles = (uint32_t)tt;
+  unsigned int* mem = nullptr;
+  ECFFT_CUDA(cudaMallocAsync((void**)&mem, ((size_t)ncounters + 1) * sizeof(unsigned int), st));
+  ECFFT_CUDA(cudaMemsetAsync(mem, 0, ((size_t)ncounters + 1) * sizeof(unsigned int), st));
+  d.queue = mem;
+  d.counters = mem + 1;
+  d.stats = g_flow_stats;
+  const bool timed = prof::enabled();
+  if (timed) prof::record_begin(prof::EXTEND_TILE, bytes, st);
+  switch (sym_variant()) {
+    case 1: launch_flow_shape<128, 4>(d, log_t, widest, st); break;
+    case 2: launch_flow_shape<256, 3>(d, log_t, widest, st); break;
+    case 3: launch_flow_shape<256, 2>(d, log_t, widest, st); break;
+    case 4: launch_flow_shape<64, 10>(d, log_t, widest, st); break;
+    default: launch_flow_shape<128, 5>(d, log_t, widest, st); break;
+  }
+  if (timed) prof::record_end(st);
+  prof::count_launch();
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(mem, st);
+  ECFFT_CUDA(e);
 }
 
 }  // namespace k

@@ -170,6 +170,11 @@ void ecfft_profile_enable(int on);
 /* sums (and clears) the records of one kernel: device ms, algorithmic bytes, launches */
 int ecfft_profile_read(int kernel, double* ms, double* alg_bytes, unsigned long long* launches);
 
+/* Diagnostics of the flow kernel (all passes of an ENTER in one persistent launch): when enabled, its CTAs
+ * accumulate {cycles waiting for input blocks, cycles in tile bodies, cycles publishing results, tiles} on the
+ * current device.  out4 (may be NULL) receives and clears the accumulators; `enable` switches them on / off. */
+int ecfft_flow_stats(int enable, unsigned long long* out4);
+
 #ifdef __cplusplus
 }
 #endif

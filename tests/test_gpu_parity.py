@@ -242,6 +242,40 @@ def test_other_butterfly_modes_match_too(mode):
     assert r.returncode == 0 and "matrix mode ok" in r.stdout, r.stdout + r.stderr
 
 
+@pytest.mark.parametrize("variant", ["0", "1"])
+def test_flow_launch_matches_oracle(variant):
+    """ECFFT_B200_FLOW=1 runs all passes of an ENTER as ONE persistent launch with per-block dependency counters
+    instead of kernel boundaries (csrc/sym_kernel.cu k_sym_flow; off by default, measured slower).  Same bits:
+    sizes that take packed tiles only, the combine-only pass (vector = tile), one, two and three outer strided
+    passes, a batch that is not a power of two (enter_range over three blocks), and the host-buffer pipeline."""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, torch, ecfft_b200\n"
+        "from oracle import oracle as O\n"
+        "n = 1 << 18\n"
+        "g = ecfft_b200.build_fftree(n, parts=ecfft_b200.PARTS_ENTER_ONLY); c = O.OracleTree.build(n, parts=1, threads=8)\n"
+        "L = ecfft_b200._lib.load(); l0 = L.ecfft_launch_count()\n"
+        "for k in (10, 11, 12, 14, 16, 17, 18):\n"
+        "    x = O.random_elements(1 << k, seed=k)\n"
+        "    xd = torch.from_numpy(x.view(np.int64)).cuda()\n"
+        "    assert (g.enter(xd).cpu().numpy().view(np.uint64) == c.enter(x, threads=8)).all(), k\n"
+        "x = O.random_elements(3 << 12, seed=5)\n"
+        "xd = torch.from_numpy(x.view(np.int64)).cuda()\n"
+        "got = g.enter_range(xd, 1, 1 << 12).cpu().numpy().view(np.uint64)\n"
+        "for b in range(3):\n"
+        "    assert (got[b << 12:(b + 1) << 12] == c.enter(x[b << 12:(b + 1) << 12])).all()\n"
+        "x = O.random_elements(n, seed=6)\n"
+        "assert (g.enter(x) == c.enter(x, threads=8)).all()\n"
+        "assert L.ecfft_launch_count() - l0 < 40, 'flow path was not taken'\n"
+        "print('flow ok')\n")
+    env = dict(os.environ, ECFFT_B200_FLOW="1", ECFFT_B200_SYM_VARIANT=variant)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "flow ok" in r.stdout, r.stdout + r.stderr
+
+
 # ---- BASELINE.json full sizes: size-independent properties (the oracle needs minutes there) ----
 @pytest.fixture(scope="module")
 def tree22():
