@@ -34,7 +34,7 @@ SYMBOLS = [
     "ecfft_mg_prescale_dev", "ecfft_mg_cross_dev", "ecfft_mg_local_dev", "ecfft_mg_combine_dev",
     "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free", "ecfft_mg_arena_reset",
     "ecfft_mg_signal_dev", "ecfft_mg_wait_dev", "ecfft_mg_arena_bytes", "ecfft_enter_peer_dev",
-    "ecfft_selftest_field", "ecfft_flow_stats",
+    "ecfft_selftest_field", "ecfft_flow_stats", "ecfft_pointwise_mul", "ecfft_pointwise_mul_dev",
 ]
 
 
@@ -82,6 +82,8 @@ def load():
     for name in ("ecfft_redc_z0", "ecfft_redc_z1"):
         getattr(L, name).argtypes = [vp, vp, vp, sz, vp]
     L.ecfft_modular_reduce.argtypes = [vp, vp, vp, vp, sz, vp]
+    L.ecfft_pointwise_mul.argtypes = [vp, vp, vp, sz, vp]
+    L.ecfft_pointwise_mul_dev.argtypes = [vp, vp, vp, sz, vp, vp]
     L.ecfft_vanish.argtypes = [vp, vp, sz, vp]
     for name in ("ecfft_enter_dev", "ecfft_exit_dev"):
         getattr(L, name).argtypes = [vp, vp, sz, vp, vp]

@@ -379,6 +379,15 @@ int ecfft_modular_reduce(const ecfft_tree* t, const uint64_t* evals, const uint6
     io.out(out, o, n);
   });
 }
+int ecfft_pointwise_mul(const ecfft_tree* t, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out) {
+  return guard([&] {
+    LOCKED_IO
+    Fp* da = io.in(a, n);
+    Fp* db = io.in(b, n);
+    k::mul_mont(da, da, db, n, io.st);
+    io.out(out, da, n);
+  });
+}
 int ecfft_vanish(const ecfft_tree* t, const uint64_t* vanish_domain, size_t n, uint64_t* out) {
   return guard([&] {
     LOCKED_IO
@@ -437,6 +446,12 @@ int ecfft_redc_z1_dev(const ecfft_tree* t, const void* d_evals, const void* d_a,
 }
 int ecfft_modular_reduce_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, const void* d_c, size_t n, void* d_out, void* stream) {
   return guard([&] { DEV_ENGINE eng.mod_user(dptr(d_evals), dptr(d_a), dptr(d_c), n, dptr(d_out)); });
+}
+int ecfft_pointwise_mul_dev(const ecfft_tree* t, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    if (n) k::mul_mont(dptr(d_out), dptr(d_a), dptr(d_b), n, eng.st);
+  });
 }
 int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* d_out, void* stream) {
   return guard([&] {

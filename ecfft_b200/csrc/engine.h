@@ -232,6 +232,7 @@ void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t 
 
 void mul_const(Fp* out, const Fp* in, Fp c, size_t n, cudaStream_t st);                       // out = in*c
 void mul_bcast(Fp* out, const Fp* in, const Fp* c, size_t len, size_t nvec, cudaStream_t st); // out[v][i] = in[v][i]*c[i]
+void mul_mont(Fp* out, const Fp* a, const Fp* b, size_t n, cudaStream_t st);                    // Montgomery product of two data vectors
 void add_bcast_scaled(Fp* out, const Fp* in, const Fp* z, Fp scale, size_t len, size_t nvec, cudaStream_t st);  // out = in + z*scale
 void deinterleave(Fp* even, Fp* odd, const Fp* in, size_t pairs, cudaStream_t st);
 void interleave(Fp* out, const Fp* even, const Fp* odd, size_t pairs, cudaStream_t st);

@@ -138,6 +138,12 @@ void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t 
 void mul_const(Fp* out, const Fp* in, Fp c, size_t n, cudaStream_t st) {
   map(n, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_load(in + i), c)); });
 }
+// out[i] = a[i] * b[i] in the Montgomery domain the API speaks (a~ b~ R^-1 = (ab)~): what ark-ff's `*` on two
+// Fp values computes; the caller-side pointwise step of polynomial multiplication (ENTER, multiply, EXIT)
+void mul_mont(Fp* out, const Fp* a, const Fp* b, size_t n, cudaStream_t st) {
+  const Fp rinv = fp_const_RINV();
+  map(n, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_mul_lazy(fp_load(a + i), fp_load(b + i)), rinv)); });
+}
 void mul_bcast(Fp* out, const Fp* in, const Fp* c, size_t len, size_t nvec, cudaStream_t st) {
   map(len * nvec, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_load(in + i), fp_load_ro(c + i % len))); });
 }

@@ -228,6 +228,11 @@ class FFTree:
     def vanish(self, vanish_domain):
         return self._call("ecfft_vanish", [vanish_domain], 2 * len(vanish_domain))
 
+    def pointwise_mul(self, a, b):
+        """a[i] * b[i] on the tree's GPU (Montgomery limbs in and out, like `*` on two ark-ff values): the step
+        between `enter` and `exit` when polynomials are multiplied through the tree"""
+        return self._call("ecfft_pointwise_mul", [a, b], len(a))
+
     def enter_range(self, data, m_lo, m_hi):
         """device-only building block of the multi-GPU ENTER (include/ecfft_b200.h)"""
         return self._dev_call(self._L.ecfft_enter_range_dev, [data], data.shape[0], (m_lo, m_hi))

@@ -89,6 +89,13 @@ int ecfft_modular_reduce(const ecfft_tree* t, const uint64_t* evals, const uint6
 /* out has 2n elements */
 int ecfft_vanish(const ecfft_tree* t, const uint64_t* vanish_domain, size_t n, uint64_t* out);      /* :313 */
 
+/* Element-wise product of two vectors of field elements: out[i] = a[i] * b[i] (what `*` on two ark-ff Fp values
+ * computes, Montgomery form in and out).  Not a method of FFTree — it is the caller-side step between ENTER
+ * and EXIT when polynomials are multiplied through the tree (reference README.md:60-63 usage pattern, the
+ * evaluate / interpolate pair of benches/comparison.rs:37-43); it runs on the handle's GPU so the evaluations
+ * never leave the device.  Any n. */
+int ecfft_pointwise_mul(const ecfft_tree* t, const uint64_t* a, const uint64_t* b, size_t n, uint64_t* out);
+
 /* ---- device-buffer variants (no PCIe traffic; enqueue only) --------------------------- */
 int ecfft_enter_dev(const ecfft_tree* t, const void* d_coeffs, size_t n, void* d_evals, void* stream);
 int ecfft_exit_dev(const ecfft_tree* t, const void* d_evals, size_t n, void* d_coeffs, void* stream);
@@ -100,6 +107,7 @@ int ecfft_redc_z1_dev(const ecfft_tree* t, const void* d_evals, const void* d_a,
 int ecfft_modular_reduce_dev(const ecfft_tree* t, const void* d_evals, const void* d_a, const void* d_c,
                              size_t n, void* d_out, void* stream);
 int ecfft_vanish_dev(const ecfft_tree* t, const void* d_domain, size_t n, void* d_out, void* stream);
+int ecfft_pointwise_mul_dev(const ecfft_tree* t, const void* d_a, const void* d_b, size_t n, void* d_out, void* stream);
 /* Multi-GPU building block (DESIGN.md "multi-GPU"): run only the bottom-up ENTER recursion
  * depths whose block size m satisfies m_lo < m <= m_hi on an array of n elements that already
  * holds n/m_lo evaluation vectors of length m_lo (m_lo = 1: raw coefficients); n may be any multiple of
