@@ -22,6 +22,7 @@ Tree::~Tree() {
   cudaSetDevice(device);
   if (build_errors) cudaFree(build_errors);
   for (void* p : owned) cudaFree(p);
+  for (void* p : owned_lazy) cudaFree(p);
   if (stream) cudaStreamDestroy(stream);
   for (cudaStream_t s : aux) cudaStreamDestroy(s);
   if (prev >= 0 && prev != device) cudaSetDevice(prev);
@@ -235,7 +236,7 @@ void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, si
 // FFTree::redc_impl, src/fftree.rs:232-259, for nvec vectors of length len sharing `a`
 // (plain form).  a0inv (= 1/a[2i], plain) may be supplied when already known.
 void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out,
-                  const Fp* c_or_null) const {
+                  const Fp* c_or_null, Fp* const* tabs_or_null, const ExitSplit* split) const {
   const Level& lv = level_for(len);
   if (len < 2) throw Error(ERR_INVALID_ARG, "redc: length must be >= 2");
   const Fp* zinv = moiety == S0 ? lv.z0_inv_s1 : lv.z1_inv_s0;
@@ -244,26 +245,33 @@ void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, s
   const uint32_t log_h = ilog2(h);
   const Moiety other = moiety == S1 ? S0 : S1;
   Fp* a0inv_own = nullptr;
-  if (!a0inv_or_null) {
+  if (!a0inv_or_null && !tabs_or_null) {
     a0inv_own = tmp(h);
     k::copy_strided(a0inv_own, a_plain, h, 2, st);
     k::batch_inverse(a0inv_own, h, st);
     a0inv_or_null = a0inv_own;
   }
   static const bool no_fuse = getenv("ECFFT_B200_NO_REDC_FUSION") != nullptr;
+  if (tabs_or_null && !(lv.sym && lv.has_norm() && k::butterfly_mode() != 0 && !no_fuse && log_h >= 1 && (nvec << log_h) >= 4))
+    throw Error(ERR_INVALID_ARG, "redc: prebuilt tables need the fused form");
   if (lv.sym && lv.has_norm() && k::butterfly_mode() != 0 && !no_fuse && log_h >= 1 && (nvec << log_h) >= 4) {
     // Fused form: the de-interleave, the two pointwise steps and the interleave ride the two EXTENDs as
     // stride-2 views and per-position tables (k_extend_sym): no pointwise pass over the data.
     //   EXTEND 1: reads evals[2i], pre-scale a0inv*gami (*c), stores out[2i+1] = evals[2i+1]*zinv(*c) - g1^*(gam*a*zinv)
     //   EXTEND 2: reads out[2i+1] (= h1), stores out[2i] = h0
-    Fp* tabs = tmp(3 * h);
+    Fp* tabs = tabs_or_null ? nullptr : tmp(3 * h);
     Fp* work = tmp(h * nvec);
-    Fp *P1 = tabs, *Kp = tabs + h, *Zc = tabs + 2 * h;
-    k::redc_tables(P1, Kp, Zc, a_plain, a0inv_or_null, zinv, lv.gami[moiety], lv.gam[other], c_or_null, h, st);
+    Fp *P1 = tabs_or_null ? tabs_or_null[0] : tabs, *Kp = tabs_or_null ? tabs_or_null[1] : tabs + h, *Zc = tabs_or_null ? tabs_or_null[2] : tabs + 2 * h;
+    if (!tabs_or_null) k::redc_tables(P1, Kp, Zc, a_plain, a0inv_or_null, zinv, lv.gami[moiety], lv.gam[other], c_or_null, h, st);
     k::SymIO io1{1, 0, 1, 1, evals, 1, 1, Zc, work};
     k::SymIO io2{1, 1, 1, 0, nullptr, 0, 0, nullptr, work};
+    if (split) {   // EXIT: the second EXTEND stores [u0 | (e0 - u0) * xnn_inv] into the next depth's array instead of out[2i]
+      io2.out_shift = 0; io2.out_off = 0;
+      io2.E = split->evals; io2.e_shift = 1; io2.e_off = 0; io2.Z = split->xinv_even;
+      io2.split = 1;
+    }
     const bool ok1 = k::extend_sym(lv.tw_d[moiety], lv.tw_r[other], lv.ctr[other], evals, out, log_h, nvec, P1, Kp, nullptr, st, &io1);
-    const bool ok2 = ok1 && k::extend_sym(lv.tw_d[other], lv.tw_r[moiety], lv.ctr[moiety], out, out, log_h, nvec, lv.gami[other], lv.gam[moiety], nullptr, st, &io2);
+    const bool ok2 = ok1 && k::extend_sym(lv.tw_d[other], lv.tw_r[moiety], lv.ctr[moiety], out, split ? split->next : out, log_h, nvec, lv.gami[other], lv.gam[moiety], nullptr, st, &io2);
     release(tabs);
     release(work);
     release(a0inv_own);
@@ -348,6 +356,35 @@ void Engine::exit(const Fp* evals, Fp* out, size_t n) const {
   release(M);
 }
 
+// The fused-REDC tables of EXIT's MOD at this level (a = xnn_s, c = z0z0_rem_xnn_s), built once per level.
+bool Engine::exit_tabs(const Level& lv) const {
+  static const bool no_fuse = getenv("ECFFT_B200_NO_REDC_FUSION") != nullptr || getenv("ECFFT_B200_NO_EXIT_TABLES") != nullptr;
+  const size_t h = (size_t)1 << (lv.log_n - 1);
+  if (no_fuse || !(lv.sym && lv.has_norm() && k::butterfly_mode() != 0) || lv.log_n < 2) return false;
+  std::lock_guard<std::mutex> lock(t.tab_mu);
+  if (lv.exit_tab[1][2]) return true;
+  // built on the tree's own stream and completed before anybody uses them (one-time cost per level)
+  cudaStream_t bs = t.stream;
+  auto alloc = [&](size_t count) {
+    void* p = nullptr;
+    ECFFT_CUDA(cudaMalloc(&p, count * sizeof(Fp)));
+    t.owned_lazy.push_back(p);
+    return (Fp*)p;
+  };
+  Fp* a0inv = alloc(h);
+  k::copy_strided(a0inv, lv.xnn_s_inv, h, 2, bs);   // the reference batch-inverts xnn_s[::2] on every call (fftree.rs:235): same values
+  Fp* tab[2][3];
+  for (int r = 0; r < 2; r++) {
+    for (int i = 0; i < 3; i++) tab[r][i] = alloc(h);
+    k::redc_tables(tab[r][0], tab[r][1], tab[r][2], lv.xnn_s, a0inv, lv.z0_inv_s1, lv.gami[S0], lv.gam[S1], r ? lv.z0z0 : nullptr, h, bs);
+  }
+  ECFFT_CUDA(cudaStreamSynchronize(bs));
+  lv.exit_a0inv = a0inv;
+  for (int r = 0; r < 2; r++)
+    for (int i = 0; i < 3; i++) lv.exit_tab[r][i] = tab[r][i];
+  return true;
+}
+
 // The passes of EXIT for block sizes m_from, m_from/2, ..., 2*m_stop on an array of len elements (len/m
 // vectors per pass), ping-ponging between cur and nxt.  Returns true when the result ended up in nxt.
 bool Engine::exit_depths(Fp* cur, Fp* nxt, Fp* M, size_t len, size_t m_from, size_t m_stop) const {
@@ -356,13 +393,29 @@ bool Engine::exit_depths(Fp* cur, Fp* nxt, Fp* M, size_t len, size_t m_from, siz
     const Level& lv = level_for(m);
     if (!lv.z0z0) throw Error(ERR_MISSING_TABLES, "exit: tree was built without the Z tables");
     const size_t h = m / 2, nvec = len / m;
-    // the reference batch-inverts xnn_s[::2] on every call (fftree.rs:235); the stored
-    // xnn_s_inv holds the same values
-    Fp* a0inv = tmp(h);
-    k::copy_strided(a0inv, lv.xnn_s_inv, h, 2, st);
-    modular_reduce(cur, lv.xnn_s, a0inv, lv.z0z0, m, nvec, M);
+    if (h >= 2 && (nvec * h) >= 4 && exit_tabs(lv)) {
+      // MOD = REDC, x c, REDC (fftree.rs:277-281) with the level's prebuilt tables: four EXTENDs, no pointwise pass
+      Fp* hb = tmp(m * nvec);
+      redc(cur, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, hb, nullptr, lv.exit_tab[0]);
+      static const bool no_split = getenv("ECFFT_B200_NO_EXIT_SPLIT_FUSION") != nullptr;
+      if (!no_split) {
+        ExitSplit sp{cur, lv.exit_a0inv, nxt};
+        redc(hb, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, M, lv.z0z0, lv.exit_tab[1], &sp);   // ... and the split rides its last EXTEND
+        release(hb);
+        std::swap(cur, nxt);
+        in_nxt = !in_nxt;
+        continue;
+      }
+      redc(hb, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, M, lv.z0z0, lv.exit_tab[1]);
+      release(hb);
+    } else {
+      // the reference batch-inverts xnn_s[::2] on every call (fftree.rs:235); the stored xnn_s_inv holds the same values
+      Fp* a0inv = tmp(h);
+      k::copy_strided(a0inv, lv.xnn_s_inv, h, 2, st);
+      modular_reduce(cur, lv.xnn_s, a0inv, lv.z0z0, m, nvec, M);
+      release(a0inv);
+    }
     k::exit_split(nxt, cur, M, lv.xnn_s_inv, h, nvec, st);
-    release(a0inv);
     std::swap(cur, nxt);
     in_nxt = !in_nxt;
   }

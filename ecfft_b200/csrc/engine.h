@@ -104,6 +104,10 @@ struct Level {
   Fp* gami[2] = {nullptr, nullptr};   // h: pre-scale of the decompose network (1/Gamma^mu_p and folded constants)
   Fp* gx = nullptr;                   // h: Gamma^1_i * xnn_s[2i+1] (ENTER combine)
   Fp* ctr[2] = {nullptr, nullptr};    // sym: 1 element, g_target/g_source at level 0 (index = target moiety)
+  // EXIT's two REDCs per depth (fftree.rs:206-210) always use a = xnn_s, c = z0z0_rem_xnn_s: their fused-REDC
+  // tables (kernels.cu redc_tables) depend on the level only and are built once, on first use (Engine::exit_tabs)
+  mutable Fp* exit_tab[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [redc 0 | redc 1 (x c)][P1, Kp, Zc], h each
+  mutable Fp* exit_a0inv = nullptr;   // xnn_s_inv[::2], h
   bool has_norm() const { return tw_r[0] && tw_r[1] && tw_d[0] && tw_d[1] && gam[0] && gam[1] && gami[0] && gami[1] && gx; }
 };
 
@@ -128,6 +132,8 @@ struct Tree {
   std::vector<void*> owned;          // device allocations to free
   mutable std::vector<cudaStream_t> aux;  // helper streams ENTER forks independent ranges onto (engine.cu)
   mutable std::mutex aux_mu;
+  mutable std::mutex tab_mu;             // guards the lazily built per-level EXIT tables
+  mutable std::vector<void*> owned_lazy;  // ... and owns them
   cudaStream_t aux_stream(int i) const;
   ~Tree();
   Fp* dalloc(size_t count);          // owned device allocation of `count` Fp
@@ -191,6 +197,9 @@ struct SymParams {
   uint32_t in_shift, in_off, out_shift, out_off, e_shift, e_off;
   const Fp* E;
   const Fp* Z;
+  // split != 0 (EXIT's last EXTEND of a depth, src/fftree.rs:206-220): u0 = x * post is stored at
+  // out[(vector << (log_h + 1)) + i] and v0 = (E[(g << e_shift) + e_off] - u0) * Z[i] at the same place + h
+  uint32_t split;
   // ---- flow fields (k_sym_flow: all passes of an ENTER in one persistent launch) ----
   uint32_t kind;              // 0: butterfly tile pass; 1: combine-only pass (in = [u1 | v1] unscaled, A = [u0 | v0])
   uint32_t tile_begin, ntiles;         // this pass's range of the flow's tile queue
@@ -217,7 +226,7 @@ void flow_stats_read(unsigned long long out4[4]);    // {wait cycles, body cycle
 // Strided views for REDC (fftree.rs:232-259): logical element g is read at in[(g << in_shift) + in_off] and
 // written at out[(g << out_shift) + out_off]; with E the store is E[(g << e_shift) + e_off] * Z[i] + x * post[i]
 // (i = position within the vector).  work: contiguous scratch of nvec * h elements for multi-pass EXTENDs.
-struct SymIO { uint32_t in_shift, in_off, out_shift, out_off; const Fp* E; uint32_t e_shift, e_off; const Fp* Z; Fp* work; };
+struct SymIO { uint32_t in_shift, in_off, out_shift, out_off; const Fp* E; uint32_t e_shift, e_off; const Fp* Z; Fp* work; uint32_t split = 0; };
 bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
                 const SymCombine* comb, cudaStream_t st, const SymIO* io = nullptr);
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
@@ -288,8 +297,11 @@ struct Engine {
   // batched primitives: nvec contiguous vectors
   void extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target) const;
   // c_or_null: evals are to be multiplied pointwise by c first (MOD's middle step, folded into the tables)
+  // EXIT (fftree.rs:206-220): the next depth's array [u0 | (e0 - u0) * xnn_inv[::2]] written by REDC's last EXTEND
+  struct ExitSplit { const Fp* evals; const Fp* xinv_even; Fp* next; };
   void redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out,
-            const Fp* c_or_null = nullptr) const;
+            const Fp* c_or_null = nullptr, Fp* const* tabs_or_null = nullptr, const ExitSplit* split = nullptr) const;  // tabs: prebuilt {P1, Kp, Zc} of the fused form
+  bool exit_tabs(const Level& lv) const;  // builds lv.exit_tab / exit_a0inv once; false: the fused REDC does not apply
   void modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, const Fp* c_plain, size_t len, size_t nvec, Fp* out) const;
 
   // the FFTree<F> surface (fftree.rs:72-316) on device buffers

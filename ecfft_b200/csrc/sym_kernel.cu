@@ -210,6 +210,15 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
       if (g >= p.total) continue;
       const uint32_t i = pos & hmask;
       Fp x = s.ld(e);
+      if (p.split) {
+        // EXIT's split fused into the depth's last EXTEND (src/fftree.rs:206-220): u0 | (e0 - u0) / x^(n/2)
+        const Fp u0 = fp_canon(fp_mul_lazy(x, fp_load_ro(p.post + i)));
+        const Fp e0 = FLOW ? fp_load_cg(p.E + ((g << p.e_shift) + p.e_off)) : fp_load(p.E + ((g << p.e_shift) + p.e_off));
+        Fp* o = p.out + ((g >> p.log_h) << (p.log_h + 1)) + i;
+        fp_store(o, u0);
+        fp_store(o + ((size_t)1 << p.log_h), fp_mul(fp_sub(e0, u0), fp_load_ro(p.Z + i)));
+        continue;
+      }
       if (p.E)
         x = fp_dot2_lazy(FLOW ? fp_load_cg(p.E + ((g << p.e_shift) + p.e_off)) : fp_load(p.E + ((g << p.e_shift) + p.e_off)), fp_load_ro(p.Z + i), x, fp_load_ro(p.post + i));
       else if (p.post)
@@ -245,6 +254,11 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__ SymParams p) {
   extern __shared__ uint4 smem_raw[];
+  // Programmatic dependent launch (ECFFT_B200_PDL=1): the next pass's CTAs may be scheduled while this grid
+  // drains — everything below still waits for the previous grid's results (griddepcontrol.wait returns once
+  // the prerequisite grid has completed and its memory is visible).  No-ops without the launch attribute.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.packed)
     sym_tile<NT, false>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t);
   else
@@ -372,15 +386,17 @@ __global__ void __launch_bounds__(NT, MINB) k_sym_flow(const __grid_constant__ F
   }
 }
 
-// Launch shapes (ECFFT_B200_SYM_VARIANT): 0 = 128 threads, 5 CTAs/SM, 1024-element tile (default);
-// 1 = 128 threads, 4 CTAs/SM; 2 = 256 threads, 3 CTAs/SM; 3 = 256 threads, 2 CTAs/SM, 2048-element tile;
+// Launch shapes (ECFFT_B200_SYM_VARIANT): 0 = 128 threads, 5 CTAs/SM (96 registers), 1024-element tile;
+// 1 = 128 threads, 4 CTAs/SM (126 registers; default); 2 = 256 threads, 3 CTAs/SM; 3 = 256 threads, 2 CTAs/SM, 2048-element tile;
 // 4 = 64 threads, 10 CTAs/SM, 512-element tile (shorter CTAs: smaller end-of-launch drain, one level less per pass).
 static int sym_variant() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ECFFT_B200_SYM_VARIANT");
-    v = e ? atoi(e) : 0;
-    if (v < 0 || v > 4) v = 0;
+    // default 1 (126 registers, 4 CTAs/SM): measured 0.5 % (n = 2^22) to 5 % (2^20) faster than shape 0 on B200
+    // (profiles/r02_e_*, r02_f_*): two products interleave without register pressure
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 4) v = 1;
   }
   return v;
 }
@@ -400,10 +416,33 @@ bool flow_enabled() {
   return v != 0;
 }
 
+static bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    // on by default: 6 % at n = 2^16, 3 % at 2^19, neutral at 2^22 (profiles/r02_g_pdl.txt)
+    const char* e = getenv("ECFFT_B200_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 template <int NT, int MINB>
 static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
   static PerDeviceOnce configured;
   configured.run([] { ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp)))); });
+  if (pdl_enabled()) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(NT);
+    cfg.dynamicSmemBytes = ((size_t)sizeof(Fp)) << p.log_t;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k_extend_sym<NT, MINB>, p));
+    return;
+  }
   k_extend_sym<NT, MINB><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
 }
 
@@ -453,6 +492,7 @@ bool plan_extend_sym(SymFlow& flow, const Fp* tw_d, const Fp* tw_r, const Fp* ct
     first_io.in_shift = io->in_shift; first_io.in_off = io->in_off;
     last_io.out_shift = io->out_shift; last_io.out_off = io->out_off;
     last_io.E = io->E; last_io.Z = io->Z; last_io.e_shift = io->e_shift; last_io.e_off = io->e_off;
+    last_io.split = io->split;
     if (io->E && !(io->Z && post)) throw Error(ERR_INVALID_ARG, "extend_sym: E needs Z and post");
     mid = io->work;
   }
@@ -461,6 +501,7 @@ bool plan_extend_sym(SymFlow& flow, const Fp* tw_d, const Fp* tw_r, const Fp* ct
   auto set_last = [&](SymParams& q) {
     q.out_shift = last_io.out_shift; q.out_off = last_io.out_off;
     q.E = last_io.E; q.Z = last_io.Z; q.e_shift = last_io.e_shift; q.e_off = last_io.e_off;
+    q.split = last_io.split;
   };
   p.tw_d = tw_d;
   p.tw_r = tw_r;

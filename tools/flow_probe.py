@@ -37,14 +37,15 @@ def main():
     launches = (L.ecfft_launch_count() - l0) / reps
     out = {"log_n": log_n, "ms": ms, "launches": launches,
            "env": {k: v for k, v in os.environ.items() if k.startswith("ECFFT_B200")}}
-    if os.environ.get("ECFFT_B200_FLOW", "1") != "0":
+    if os.environ.get("ECFFT_B200_FLOW", "0") != "0":
         _lib.check(L.ecfft_flow_stats(1, None))
         for i in range(4):
             tree.enter(xs[i % 2])
         st = (ctypes.c_ulonglong * 4)()
         _lib.check(L.ecfft_flow_stats(0, st))
         wait, body, sig, tiles = [int(v) for v in st]
-        tot = wait + body + sig
+        tot = max(wait + body + sig, 1)
+        tiles = max(tiles, 1)
         out.update({"tiles_per_enter": tiles / 4, "wait_frac": wait / tot, "body_frac": body / tot, "sig_frac": sig / tot,
                     "wait_cycles_per_tile": wait / tiles, "body_cycles_per_tile": body / tiles, "sig_cycles_per_tile": sig / tiles})
     print(json.dumps(out), flush=True)
