@@ -455,7 +455,7 @@ def main():
     if not args.no_configs:
         cfg = run_configs(args, tree, world, rank, local_rank, dev, timed, all_ranks_true)
         line.update(cfg)
-        ok_all = ok_all and all(v for k, v in cfg.items() if k.endswith("_matches_single") or k.endswith("_roundtrip_ok"))
+        ok_all = ok_all and all(v for k, v in cfg.items() if k.endswith("_matches_single") or k.endswith("_roundtrip_ok") or k.endswith("_status_ok"))
     if "multi_gpu_matches_single" in line:
         ok_all = ok_all and line["multi_gpu_matches_single"]
 
@@ -552,6 +552,26 @@ def run_configs(args, tree22, world, rank, local_rank, dev, timed, all_ranks_tru
     out["cfg_2p24_matches_single"] = all_ranks_true(bool((got == want).all()))
     out["cfg_2p24_single_gpu_ms"] = median_ms(lambda: tree.enter(full), warm=1, reps=3)
     import torch.distributed as dist
+    dist.barrier()
+    arena.close()
+    del tree, full, mine, got, want
+    torch.cuda.empty_cache()
+
+    # sharded EXIT at the headline size (reference src/fftree.rs:200-224): MOD across the ranks for the top
+    # log2(N) depths, then an independent EXIT(n/N) per rank; checked against a single-GPU EXIT on every rank
+    from ecfft_b200.dist import exit_sharded_peer
+    ne = 1 << args.log_n
+    tree = ecfft_b200.build_fftree(ne, device=local_rank)
+    ev = to_dev(O.random_elements(ne, seed=22))
+    ce = ne // world
+    mine = ev[rank * ce:(rank + 1) * ce].contiguous()
+    arena = PeerArena.create(ne, local_rank)
+    out[f"cfg_exit_sharded_2p{args.log_n}_ms"] = median_ms(lambda: exit_sharded_peer(tree, mine, ne, arena, gather=False), warm=2, reps=5)
+    got = exit_sharded_peer(tree, mine, ne, arena)
+    want = tree.exit(ev)
+    out[f"cfg_exit_sharded_2p{args.log_n}_matches_single"] = all_ranks_true(bool((got == want).all()))
+    out[f"cfg_exit_single_gpu_2p{args.log_n}_ms"] = median_ms(lambda: tree.exit(ev), warm=1, reps=3)
+    out[f"cfg_exit_sharded_2p{args.log_n}_arena_status_ok"] = all_ranks_true(arena.status() == 0)
     dist.barrier()
     arena.close()
     return out

@@ -32,9 +32,10 @@ SYMBOLS = [
     "ecfft_modular_reduce_dev", "ecfft_vanish_dev", "ecfft_enter_range_dev",
     "ecfft_launch_count", "ecfft_profile_enable", "ecfft_profile_read",
     "ecfft_mg_prescale_dev", "ecfft_mg_cross_dev", "ecfft_mg_local_dev", "ecfft_mg_combine_dev",
-    "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free", "ecfft_mg_arena_reset",
+    "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free", "ecfft_mg_arena_reset", "ecfft_mg_arena_status",
     "ecfft_mg_signal_dev", "ecfft_mg_wait_dev", "ecfft_mg_arena_bytes", "ecfft_enter_peer_dev",
     "ecfft_selftest_field", "ecfft_flow_stats", "ecfft_pointwise_mul", "ecfft_pointwise_mul_dev",
+    "ecfft_mg_exit_arena_bytes", "ecfft_exit_peer_dev",
 ]
 
 
@@ -104,9 +105,12 @@ def load():
     L.ecfft_mg_arena_close.argtypes = [vp]
     L.ecfft_mg_arena_free.argtypes = [vp]
     L.ecfft_mg_arena_reset.argtypes = [vp, vp]
+    L.ecfft_mg_arena_status.argtypes = [vp, ctypes.POINTER(ctypes.c_ulonglong)]
     L.ecfft_selftest_field.argtypes = [ci, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong)]
     L.ecfft_mg_arena_bytes.argtypes = [sz, ci, psz]
     L.ecfft_enter_peer_dev.argtypes = [vp, vp, sz, ci, ci, pvp, ctypes.c_ulonglong, vp, vp]
+    L.ecfft_exit_peer_dev.argtypes = [vp, vp, sz, ci, ci, pvp, ctypes.c_ulonglong, vp, vp]
+    L.ecfft_mg_exit_arena_bytes.argtypes = [sz, ci, psz]
     L.ecfft_mg_signal_dev.argtypes = [vp, ctypes.c_ulonglong, vp]
     L.ecfft_mg_wait_dev.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_uint, vp]
     L.ecfft_flow_stats.argtypes = [ci, ctypes.POINTER(ctypes.c_ulonglong)]

@@ -546,6 +546,12 @@ int ecfft_mg_arena_close(void* d_peer_ptr) {
 int ecfft_mg_arena_free(void* d_ptr) {
   return guard([&] { ECFFT_CUDA(cudaFree(d_ptr)); });
 }
+int ecfft_mg_arena_status(const void* d_ptr, unsigned long long* status) {
+  return guard([&] {
+    require(d_ptr != nullptr && status != nullptr, ERR_INVALID_ARG, "null argument");
+    ECFFT_CUDA(cudaMemcpy(status, (const unsigned long long*)d_ptr + MG_STATUS_FLAG, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  });
+}
 int ecfft_mg_arena_reset(void* d_ptr, void* stream) {
   return guard([&] {
     require(d_ptr != nullptr, ERR_INVALID_ARG, "null arena");
@@ -579,6 +585,20 @@ int ecfft_enter_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int
     DEV_ENGINE
     require(arena_bases != nullptr, ERR_INVALID_ARG, "null arena table");
     enter_peer(eng, dptr(d_chunk), n, rank, world, arena_bases, epoch, dptr(d_out_chunk));
+  });
+}
+int ecfft_mg_exit_arena_bytes(size_t n, int world, size_t* bytes) {
+  return guard([&] {
+    require(bytes != nullptr, ERR_INVALID_ARG, "null output");
+    *bytes = peer_exit_arena_bytes(n, world);
+  });
+}
+int ecfft_exit_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
+                        unsigned long long epoch, void* d_out_chunk, void* stream) {
+  return guard([&] {
+    DEV_ENGINE
+    require(arena_bases != nullptr, ERR_INVALID_ARG, "null arena table");
+    exit_peer(eng, dptr(d_chunk), n, rank, world, arena_bases, epoch, dptr(d_out_chunk));
   });
 }
 int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream) {

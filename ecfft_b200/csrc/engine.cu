@@ -365,9 +365,11 @@ bool Engine::exit_tabs(const Level& lv) const {
   if (lv.exit_tab[1][2]) return true;
   // built on the tree's own stream and completed before anybody uses them (one-time cost per level)
   cudaStream_t bs = t.stream;
+  // stream-ordered allocation: cudaMalloc may synchronise the whole device, which must not happen while another
+  // rank's stream of this process waits for work this thread has yet to enqueue (virtual ranks on one GPU)
   auto alloc = [&](size_t count) {
     void* p = nullptr;
-    ECFFT_CUDA(cudaMalloc(&p, count * sizeof(Fp)));
+    ECFFT_CUDA(cudaMallocAsync(&p, count * sizeof(Fp), bs));
     t.owned_lazy.push_back(p);
     return (Fp*)p;
   };

@@ -161,7 +161,7 @@ namespace k {
 // the final Gamma scaling to the caller (ENTER folds it into its combine).
 void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, Moiety target, cudaStream_t st,
             bool unscaled_out = false);
-void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st, const Fp* pre = nullptr);
+void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st, const Fp* pre = nullptr, Moiety source = S0, Moiety target = S1);
 // sym_kernel.cu: all passes of the symmetric-butterfly EXTEND (tw_d = 1/g of the source moiety, tw_r = g of
 // the target moiety, ctr = Level::ctr[target]; pre/post = per-position scales or null).  comb != null fuses ENTER's combine
 // (fftree.rs:155-159) into the last pass: vectors 2w, 2w+1 are u, v of block w, comb->A the depth's
@@ -229,10 +229,14 @@ void flow_stats_read(unsigned long long out4[4]);    // {wait cycles, body cycle
 struct SymIO { uint32_t in_shift, in_off, out_shift, out_off; const Fp* E; uint32_t e_shift, e_off; const Fp* Z; Fp* work; uint32_t split = 0; };
 bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
                 const SymCombine* comb, cudaStream_t st, const SymIO* io = nullptr);
-void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st);
+void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st,
+              Moiety source = S0, Moiety target = S1);
+void dot2_strided(Fp* out, const Fp* e, size_t e_stride, const Fp* z, const Fp* g, const Fp* kp, size_t n, cudaStream_t st);
+void sub_mul_strided(Fp* out, const Fp* a, size_t a_stride, const Fp* b, const Fp* c, size_t n, cudaStream_t st);
 void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
-             const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st);
-void mg_wait_all(void* const* bases, int world, int rank, unsigned idx, unsigned long long value, unsigned timeout_ms, cudaStream_t st);
+             const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st, unsigned long long* status = nullptr, unsigned info = 0);
+void mg_wait_all(void* const* bases, int world, int rank, unsigned idx, unsigned long long value, unsigned timeout_ms, cudaStream_t st,
+                 unsigned long long* status = nullptr);
 void mg_combine(const Level& lv, size_t i0, const Fp* u0, const Fp* v0, const Fp* u1, const Fp* v1, size_t count, Fp* out, cudaStream_t st);
 int butterfly_mode();  // ECFFT_B200_BUTTERFLY: 2 = symmetric (default), 1 = normalised, 0 = 2x2 matrices
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
@@ -324,10 +328,17 @@ struct Engine {
 // [rank n/world, (rank+1) n/world)) to out_chunk.
 static constexpr size_t MG_FLAG_BYTES = 4096;
 static constexpr unsigned MG_DONE_FLAG = MG_FLAG_BYTES / 8 - 1;  // "this rank has finished call `epoch`"
+static constexpr unsigned MG_STATUS_FLAG = MG_FLAG_BYTES / 8 - 2;  // 0, or the record of the first wait that timed out
 size_t peer_arena_bytes(size_t n, int world);
 unsigned peer_timeout_ms();  // ECFFT_B200_PEER_TIMEOUT_MS (default 20000, 0 = wait for ever)
 void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int world, void* const* bases,
                 unsigned long long epoch, Fp* out_chunk);
+// EXIT (fftree.rs:200-224) the same way: rank `rank` holds evaluations [rank n/world, (rank+1) n/world) and ends
+// with coefficients of the same range; the top log2(world) depths run MOD across the ranks, then every rank
+// runs an independent EXIT(n/world).  Needs peer_exit_arena_bytes.
+size_t peer_exit_arena_bytes(size_t n, int world);
+void exit_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int world, void* const* bases,
+               unsigned long long epoch, Fp* out_chunk);
 
 // ---- builder.cu / serialize.cu --------------------------------------------------------------
 Tree* build_secp256k1(size_t n, int parts, int device);                                     // lib.rs:39-85

@@ -412,8 +412,9 @@ void build_matrices(Fp* rl, Fp* dl, const Fp* flayer, size_t fstride, size_t d, 
 // ENTER combine on a slice.  `own`/`partner` are the two ranks' chunks of the same vector, element e of
 // both belonging to the same pair; role 0: own holds the lower (p) element, 1: the upper (q) element.
 // ------------------------------------------------------------------------------------------
-void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st) {
-  const Fp* table = phase == 0 ? lv.tw_d[0] : lv.tw_r[1];
+void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st,
+              Moiety source, Moiety target) {
+  const Fp* table = phase == 0 ? lv.tw_d[source] : lv.tw_r[target];
   if (!table) throw Error(ERR_MISSING_TABLES, "mg_cross: normalised tables missing");
   const size_t mask = ((size_t)1 << j) - 1, ibase = p_pos0 & mask;
   if (lv.sym) {  // symmetric form: one twiddle per pair
@@ -450,8 +451,19 @@ void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, c
 // `value` in own_flag (release at system scope: everything enqueued before is visible to the node), then
 // spin until each given peer flag shows >= value.  A wait not satisfied within the timeout traps — a CUDA
 // error on the next call instead of a hung GPU.
+// A wait that is not satisfied within the timeout records {1<<63 | value << 24 | info << 8 | which} in *status (the
+// waiting rank's own arena; first record wins; ecfft_mg_arena_status reads it) and then traps — unless
+// ECFFT_B200_PEER_NO_TRAP is set, in which case the kernel gives up waiting and the call's results are garbage
+// that the caller detects through the status word.
+__device__ __forceinline__ void mg_timeout(unsigned long long* status, unsigned long long value, unsigned info, unsigned which, int no_trap) {
+  if (status) {
+    atomicCAS(status, 0ull, (1ull << 63) | (value << 24) | ((unsigned long long)(info & 0xffff) << 8) | (which & 0xff));
+    __threadfence_system();
+  }
+  if (!no_trap) __trap();
+}
 __global__ void k_mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
-                          const unsigned long long* wait_b, unsigned long long timeout_ns) {
+                          const unsigned long long* wait_b, unsigned long long timeout_ns, unsigned long long* status, unsigned info, int no_trap) {
   if (own_flag) {
     __threadfence_system();
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(own_flag), "l"(value) : "memory");
@@ -465,7 +477,10 @@ __global__ void k_mg_sync(unsigned long long* own_flag, unsigned long long value
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(w[i]) : "memory");
       if (v >= value) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (timeout_ns && t - t0 > timeout_ns) __trap();  // 0 = wait for ever
+      if (timeout_ns && t - t0 > timeout_ns) {  // 0 = wait for ever
+        mg_timeout(status, value, info, (unsigned)i, no_trap);
+        break;
+      }
       __nanosleep(100);
     }
   }
@@ -473,7 +488,8 @@ __global__ void k_mg_sync(unsigned long long* own_flag, unsigned long long value
 }
 // all-peers form: spin until flag[idx] of every other rank's arena shows >= value
 struct ArenaBases { const unsigned long long* base[16]; };
-__global__ void k_mg_wait_all(ArenaBases b, int world, int rank, unsigned idx, unsigned long long value, unsigned long long timeout_ns) {
+__global__ void k_mg_wait_all(ArenaBases b, int world, int rank, unsigned idx, unsigned long long value, unsigned long long timeout_ns,
+                              unsigned long long* status, int no_trap) {
   unsigned long long t0, t, v;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
   for (int r = 0; r < world; r++) {
@@ -482,23 +498,32 @@ __global__ void k_mg_wait_all(ArenaBases b, int world, int rank, unsigned idx, u
       asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(b.base[r] + idx) : "memory");
       if (v >= value) break;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-      if (timeout_ns && t - t0 > timeout_ns) __trap();  // 0 = wait for ever
+      if (timeout_ns && t - t0 > timeout_ns) {  // 0 = wait for ever
+        mg_timeout(status, value, 0xffffu, (unsigned)r, no_trap);
+        break;
+      }
       __nanosleep(100);
     }
   }
   __threadfence_system();
 }
-void mg_wait_all(void* const* bases, int world, int rank, unsigned idx, unsigned long long value, unsigned timeout_ms, cudaStream_t st) {
+static int peer_no_trap() {
+  static int v = -1;
+  if (v < 0) v = getenv("ECFFT_B200_PEER_NO_TRAP") != nullptr;
+  return v;
+}
+void mg_wait_all(void* const* bases, int world, int rank, unsigned idx, unsigned long long value, unsigned timeout_ms, cudaStream_t st,
+                 unsigned long long* status) {
   if (world > 16) throw Error(ERR_INVALID_ARG, "peer schedule supports at most 16 ranks");
   ArenaBases b{};
   for (int r = 0; r < world; r++) b.base[r] = (const unsigned long long*)bases[r];
-  k_mg_wait_all<<<1, 1, 0, st>>>(b, world, rank, idx, value, (unsigned long long)timeout_ms * 1000000ull);
+  k_mg_wait_all<<<1, 1, 0, st>>>(b, world, rank, idx, value, (unsigned long long)timeout_ms * 1000000ull, status, peer_no_trap());
   prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
 void mg_sync(unsigned long long* own_flag, unsigned long long value, const unsigned long long* wait_a,
-             const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st) {
-  k_mg_sync<<<1, 1, 0, st>>>(own_flag, value, wait_a, wait_b, (unsigned long long)timeout_ms * 1000000ull);
+             const unsigned long long* wait_b, unsigned timeout_ms, cudaStream_t st, unsigned long long* status, unsigned info) {
+  k_mg_sync<<<1, 1, 0, st>>>(own_flag, value, wait_a, wait_b, (unsigned long long)timeout_ms * 1000000ull, status, info, peer_no_trap());
   prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
 }
@@ -675,6 +700,16 @@ void selftest_field(unsigned long long* counters, unsigned long long n, cudaStre
   k_selftest_addsub<<<148 * 8, 256, 0, st>>>(counters, n);
   prof::count_launch();
   ECFFT_CUDA(cudaGetLastError());
+}
+// out[i] = e[i * e_stride] * z[i] + g[i] * kp[i]   (REDC's h1 on a chunk, fftree.rs:253-255 with the folded tables)
+void dot2_strided(Fp* out, const Fp* e, size_t e_stride, const Fp* z, const Fp* g, const Fp* kp, size_t n, cudaStream_t st) {
+  map(n, st, [=] __device__(size_t i) {
+    fp_store(out + i, fp_canon(fp_dot2_lazy(fp_load(e + i * e_stride), fp_load_ro(z + i), fp_load(g + i), fp_load_ro(kp + i))));
+  });
+}
+// out[i] = (a[i * a_stride] - b[i]) * c[i]   (EXIT's v0 on a chunk, fftree.rs:215-219)
+void sub_mul_strided(Fp* out, const Fp* a, size_t a_stride, const Fp* b, const Fp* c, size_t n, cudaStream_t st) {
+  map(n, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_sub(fp_load(a + i * a_stride), fp_load(b + i)), fp_load_ro(c + i))); });
 }
 void mul_strided(Fp* out, const Fp* a, const Fp* b, size_t b_stride, size_t b_off, size_t n, cudaStream_t st) {
   map(n, st, [=] __device__(size_t i) { fp_store(out + i, fp_mul(fp_load(a + i), fp_load(b + b_off + i * b_stride))); });

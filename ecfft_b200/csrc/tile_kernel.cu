@@ -314,20 +314,20 @@ void extend(const Level& lv, const Fp* in, Fp* out, uint32_t log_h, size_t nvec,
 // EXTEND -> S1 of a longer vector whose contiguous chunk of 2^log_len elements this rank holds.
 // Twiddles depend only on the position modulo the half-stride, so the chunk behaves like a vector of
 // its own length with the long vector's tables; the diagonal scalings are applied by the caller.
-void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st, const Fp* pre) {
+void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaStream_t st, const Fp* pre, Moiety source, Moiety target) {
   if (!lv.has_norm()) throw Error(ERR_MISSING_TABLES, "extend_sub: normalised tables missing");
   if (log_len == 0) {
     if (pre) mul_bcast(out, in, pre, 1, 1, st);
     else if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
   }
-  if (lv.sym && extend_sym(lv.tw_d[0], lv.tw_r[1], lv.ctr[1], in, out, log_len, 1, pre, nullptr, nullptr, st)) return;
+  if (lv.sym && extend_sym(lv.tw_d[source], lv.tw_r[target], lv.ctr[target], in, out, log_len, 1, pre, nullptr, nullptr, st)) return;
   TileParams p;
   p.mode = lv.sym ? 2 : 1;
-  p.dmat = lv.tw_d[0];
-  p.rmat = lv.tw_r[1];
-  p.skip_d = 0;
-  p.skip_r = 1;
+  p.dmat = lv.tw_d[source];
+  p.rmat = lv.tw_r[target];
+  p.skip_d = target == S0 ? 1 : 0;
+  p.skip_r = target == S1 ? 1 : 0;
   run_passes(p, in, out, log_len, 1, pre, nullptr, st);
 }
 

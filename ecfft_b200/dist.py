@@ -172,9 +172,11 @@ class PeerArena:
 
     @staticmethod
     def nbytes(n, world):
-        size = ctypes.c_size_t()
-        _lib.check(_lib.load().ecfft_mg_arena_bytes(n, world, ctypes.byref(size)))   # what ecfft_enter_peer_dev needs
-        return max(size.value, _FLAG_BYTES + _peer_slots(world) * (n // world) * 32)
+        L = _lib.load()
+        size, size_exit = ctypes.c_size_t(), ctypes.c_size_t()
+        _lib.check(L.ecfft_mg_arena_bytes(n, world, ctypes.byref(size)))            # what ecfft_enter_peer_dev needs
+        _lib.check(L.ecfft_mg_exit_arena_bytes(n, world, ctypes.byref(size_exit)))  # ... and ecfft_exit_peer_dev
+        return max(size.value, size_exit.value, _FLAG_BYTES + _peer_slots(world) * (n // world) * 32)
 
     @classmethod
     def create(cls, n, device, group=None):
@@ -211,6 +213,12 @@ class PeerArena:
 
     def flag(self, r, sid):
         return self.bases[r] + 8 * sid
+
+    def status(self):
+        """0, or the record of the first flag wait on this rank that timed out (include/ecfft_b200.h)"""
+        s = ctypes.c_ulonglong()
+        _lib.check(_lib.load().ecfft_mg_arena_status(ctypes.c_void_p(self.own), ctypes.byref(s)))
+        return s.value
 
     def close(self):
         L = _lib.load()
@@ -339,4 +347,26 @@ def enter_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gathe
     if out_t is None:                                           # world == 1
         out_t = torch.empty((c, 4), dtype=chunk.dtype, device=chunk.device)
         _lib.check(L.ecfft_enter_range_dev(h, vp(arena.slot(rank, 0)), c, c, c, vp(out_t.data_ptr()), st))
+    return _finish_peer(out_t, n, world, group, gather, all_gather)
+
+
+def exit_sharded_peer(tree, chunk, n, arena, group=None, gather=True, all_gather=None):
+    """Fully sharded EXIT with peer-memory exchange (reference src/fftree.rs:200-224; csrc/sharded.cu exit_peer).
+    chunk: this rank's n/G evaluations (CUDA tensor, rank order = leaf order).  Returns the full (n, 4) coefficient
+    vector on every rank (gather=True) or this rank's chunk of it.  Shares the arena (and its epoch counter) with
+    `enter_sharded_peer`; the tree must carry all tables (PARTS_FULL)."""
+    L = _lib.load()
+    world, rank = arena.world, arena.rank
+    _check(n, world, chunk)
+    if arena.n != n:
+        raise ValueError("arena was created for a different n")
+    if world > 1 and n // world < 4:
+        raise ValueError("the sharded EXIT needs at least 4 evaluations per rank")
+    chunk = chunk.contiguous()
+    arena.epoch += 1
+    out_t = torch.empty((n // world, 4), dtype=chunk.dtype, device=chunk.device)
+    bases = (ctypes.c_void_p * world)(*arena.bases)
+    _lib.check(L.ecfft_exit_peer_dev(tree._h, ctypes.c_void_p(chunk.data_ptr()), n, rank, world, bases, arena.epoch,
+                                     ctypes.c_void_p(out_t.data_ptr()),
+                                     ctypes.c_void_p(torch.cuda.current_stream(chunk.device).cuda_stream)))
     return _finish_peer(out_t, n, world, group, gather, all_gather)

@@ -150,6 +150,11 @@ int ecfft_mg_arena_open(int device, const unsigned char* handle64, void** d_peer
 int ecfft_mg_arena_close(void* d_peer_ptr);
 int ecfft_mg_arena_free(void* d_ptr);
 int ecfft_mg_arena_reset(void* d_ptr, void* stream);
+/* 0, or the record of the first wait of ecfft_enter_peer_dev / ecfft_exit_peer_dev on this rank that timed out:
+ * bit 63 set, bits 24.. the epoch, bits 8..23 the synchronisation step (0xffff: the wait for the previous call's
+ * end), bits 0..7 which peer.  By default such a wait also traps; with ECFFT_B200_PEER_NO_TRAP set it gives up
+ * instead and the caller must check this word (synchronises with the device). */
+int ecfft_mg_arena_status(const void* d_ptr, unsigned long long* status);
 int ecfft_mg_signal_dev(void* d_flag, unsigned long long value, void* stream);
 int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned timeout_ms, void* stream);
 /* The whole per-rank schedule of the sharded ENTER in one call (reference src/fftree.rs:143-161 for the
@@ -161,6 +166,16 @@ int ecfft_mg_wait_dev(const void* d_flag, unsigned long long value, unsigned tim
  * flag of each arena), so no host barrier is needed between calls. */
 int ecfft_enter_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
                          unsigned long long epoch, void* d_out_chunk, void* stream);
+
+/* EXIT the same way (reference src/fftree.rs:200-224): d_chunk holds evaluations [rank n/world, (rank+1) n/world),
+ * d_out_chunk receives the coefficients of the same range.  The top log2(world) depths run MOD (src/fftree.rs:277-281)
+ * on vectors spread over the ranks — the butterfly levels whose pairs straddle two ranks read the partner's
+ * operands from its arena — then split (u0 | v0), each half going to half of the ranks; below, every rank runs an
+ * independent EXIT(n/world).  The arenas must hold ecfft_mg_exit_arena_bytes(n, world); epochs are shared with
+ * ecfft_enter_peer_dev (one counter per arena set, growing by one per call of either kind).  Needs a full tree. */
+int ecfft_mg_exit_arena_bytes(size_t n, int world, size_t* bytes);
+int ecfft_exit_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int rank, int world, void* const* arena_bases,
+                        unsigned long long epoch, void* d_out_chunk, void* stream);
 
 /* Device self-test of the field routines the butterflies use for a + b and a - b on unreduced operands
  * (the replacement of ark-ff's add/sub at src/utils.rs:341-346): `samples` directed operand pairs that

@@ -577,3 +577,56 @@ def test_peer_memory_schedule_with_virtual_ranks(trees, oracle_mod, world):
         eq(part, want[rank * c:(rank + 1) * c])
     for a in arenas:
         a.close()
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_exit_with_virtual_ranks(trees, oracle_mod, world):
+    """ecfft_b200.dist.exit_sharded_peer (csrc/sharded.cu exit_peer; reference src/fftree.rs:200-224): the top
+    log2(world) depths run MOD on vectors spread over `world` virtual ranks (threads, one stream each, arenas on
+    ONE GPU), cross-rank butterfly levels reading the partner's arena, then the (u0 | v0) split moves each half
+    to half of the ranks.  Against the oracle's EXIT, for evaluations of a polynomial and for arbitrary values;
+    ENTER and EXIT calls interleave on the same arenas (shared epoch counter)."""
+    import threading
+    import torch
+    from ecfft_b200.dist import PeerArena, enter_sharded_peer, exit_sharded_peer
+    gpu, cpu = trees
+    n = 1 << 14
+    coeffs = oracle_mod.random_elements(n, seed=70 + world)
+    evals = cpu.enter(coeffs)
+    arbitrary = oracle_mod.random_elements(n, seed=80 + world)
+    want_arb = cpu.exit(arbitrary)
+    ed = torch.from_numpy(evals.view(np.int64)).cuda()
+    ad = torch.from_numpy(arbitrary.view(np.int64)).cuda()
+    cd = torch.from_numpy(coeffs.view(np.int64)).cuda()
+    c = n // world
+    arenas = PeerArena.local_group(n, world, device=0)
+    results, errors = [None] * world, []
+    torch.cuda.synchronize()
+
+    def run(rank):
+        try:
+            stream = torch.cuda.Stream()
+            with torch.cuda.stream(stream):
+                sl = slice(rank * c, (rank + 1) * c)
+                back = exit_sharded_peer(gpu, ed[sl], n, arenas[rank], gather=False)
+                again = enter_sharded_peer(gpu, cd[sl], n, arenas[rank], gather=False)      # ENTER on the same arenas
+                arb = exit_sharded_peer(gpu, ad[sl], n, arenas[rank], gather=False)
+                stream.synchronize()
+                results[rank] = tuple(t.cpu().numpy().view(np.uint64) for t in (back, again, arb))
+        except Exception as e:
+            errors.append(repr(e))
+
+    threads = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join(timeout=300)
+    assert not errors, errors
+    for rank in range(world):
+        sl = slice(rank * c, (rank + 1) * c)
+        back, again, arb = results[rank]
+        eq(back, coeffs[sl])
+        eq(again, evals[sl])
+        eq(arb, want_arb[sl])
+    for a in arenas:
+        a.close()

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 import ecfft_b200
-from ecfft_b200.dist import PeerArena, enter_sharded, enter_sharded_allgather, enter_sharded_peer
+from ecfft_b200.dist import PeerArena, enter_sharded, enter_sharded_allgather, enter_sharded_peer, exit_sharded_peer
 from oracle import oracle as O
 
 
@@ -21,7 +21,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
-    tree = ecfft_b200.build_fftree(n, parts=ecfft_b200.PARTS_ENTER_ONLY, device=local)
+    tree = ecfft_b200.build_fftree(n, device=local)
     x = torch.from_numpy(O.random_elements(n, seed=9).view(np.int64)).to(dev)
     want = tree.enter(x)
     c = n // world
@@ -34,6 +34,11 @@ def main():
     ok = ok and bool((enter_sharded_peer(tree, chunk, n, arena, native=False) == want).all())   # step-by-step driver
     part = enter_sharded_peer(tree, chunk, n, arena, gather=False)
     ok = ok and bool((part == want[rank * c:(rank + 1) * c]).all())
+    # sharded EXIT on the same arenas: inverse of the sharded ENTER, and arbitrary values against single-GPU EXIT
+    back = exit_sharded_peer(tree, want[rank * c:(rank + 1) * c].contiguous(), n, arena, gather=False)
+    ok = ok and bool((back == chunk).all())
+    ok = ok and bool((exit_sharded_peer(tree, chunk, n, arena) == tree.exit(x)).all())
+    ok = ok and arena.status() == 0
     ok_nccl = bool((enter_sharded(tree, chunk, n) == want).all()) and bool((enter_sharded_allgather(tree, chunk, n) == want).all())
     torch.cuda.synchronize()
     print(f"rank {rank}/{world} n=2^{log_n}: peer {'OK' if ok else 'MISMATCH'}, nccl schedules {'OK' if ok_nccl else 'MISMATCH'}", flush=True)
