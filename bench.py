@@ -376,30 +376,39 @@ def main():
         h2d = d2h = n * 32
         last_e2e_in = (args.steps - 1) % NBUF
     else:
-        # every rank uploads its n/N coefficients from pinned memory, the ranks run the sharded ENTER, and EVERY
-        # rank downloads the WHOLE evaluation vector into its own pinned memory (the reference returns a whole
-        # Vec<F>); the variant where the host-side result stays sharded is reported as e2e_sharded_ms_per_step
+        # every rank uploads its n/N coefficients from pinned memory, the ranks run the sharded ENTER and gather,
+        # and RANK 0 downloads the WHOLE evaluation vector into its pinned memory — one consumer process ends up
+        # with the whole Vec<F>, as the caller of the reference does.  Variants: the host-side result stays
+        # sharded (e2e_sharded_ms_per_step), every rank downloads the whole vector (e2e_all_ranks_full_ms_per_step).
         host_chunks = [h[rank * chunk:(rank + 1) * chunk] for h in host_in]
 
-        def e2e_loop(gather):
+        def e2e_loop(gather, everyone=False):
+            download = gather and (everyone or rank == 0)
             host_out = torch.empty((n if gather else chunk, 4), dtype=torch.int64).pin_memory()
             if args.multi_gpu == "allgather":
                 fn = (lambda x_: enter_sharded_allgather(tree, x_, n)) if gather else (lambda x_: enter_sharded_allgather(tree, x_, n)[rank * chunk:(rank + 1) * chunk])
             else:
                 fn = lambda x_: shard_fn(tree, x_, n, gather=gather)
             for i in range(2):
-                host_out.copy_(fn(host_chunks[i % NBUF].to(dev, non_blocking=True)), non_blocking=True)
+                res = fn(host_chunks[i % NBUF].to(dev, non_blocking=True))
+                if download or not gather:
+                    host_out.copy_(res, non_blocking=True)
             barrier()
             t0 = time.perf_counter()
             for i in range(args.steps):
                 xd = host_chunks[i % NBUF].to(dev, non_blocking=True)
-                host_out.copy_(fn(xd), non_blocking=True)
+                res = fn(xd)
+                if download or not gather:
+                    host_out.copy_(res, non_blocking=True)
                 torch.cuda.synchronize()
+                if gather and world > 1:
+                    dist.barrier()      # a step ends when rank 0 holds the whole result
             barrier()
             return max_over_ranks((time.perf_counter() - t0) / args.steps)
 
         e2e_s = e2e_loop(True)
         extra["e2e_sharded_ms_per_step"] = e2e_loop(False) * 1e3
+        extra["e2e_all_ranks_full_ms_per_step"] = e2e_loop(True, everyone=True) * 1e3
         h2d, d2h = chunk * 32, n * 32
     clocks = sampler.stop()
 
@@ -422,7 +431,7 @@ def main():
         "e2e": {"value": n / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_s * 1e3,
                 "path": ("ecfft_enter (host-buffer C ABI): pinned host coefficients -> H2D -> ENTER -> D2H -> pinned host evaluations" if world == 1
-                         else "per rank: pinned host chunk (n/N coefficients) -> H2D -> sharded ENTER -> all-gather -> D2H of the WHOLE evaluation vector into every rank's pinned memory; bytes are per rank")},
+                         else "every rank: pinned host chunk (n/N coefficients) -> H2D -> sharded ENTER -> all-gather; rank 0: D2H of the WHOLE evaluation vector into its pinned memory (h2d bytes per rank, d2h bytes on rank 0)")},
         "gpu_launches": int(launches),
         "roofline": {
             "kernel": "k_extend_sym", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

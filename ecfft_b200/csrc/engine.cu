@@ -62,22 +62,25 @@ void Engine::extend(const Fp* in, Fp* out, size_t h, size_t nvec, Moiety target)
 // Number of concurrent streams ENTER spreads independent coefficient ranges over (ECFFT_B200_ENTER_STREAMS,
 // default 2): the ranges do not interact below block size n/S, and kernels of different streams fill each
 // other's end-of-launch drain (a launch loses about half a CTA lifetime of SM occupancy while it drains).
-static int enter_streams() {
+// Default: two streams from 2^21 elements up, four for 2^19 .. 2^20 (launches of such sizes do not fill the GPU
+// on their own: measured 1.97 -> 1.89 ms at 2^19, 3.48 -> 3.42 ms at 2^20, but 14.7 -> 14.9 ms at 2^22;
+// profiles/r02_e_*, r02_f_*).
+static int enter_streams(size_t n = (size_t)1 << 22) {
   static int s = -1;
   if (s < 0) {
     const char* e = getenv("ECFFT_B200_ENTER_STREAMS");
-    s = e ? atoi(e) : 2;
-    if (s != 1 && s != 2 && s != 4) s = 2;
+    s = e ? atoi(e) : 0;
+    if (s != 1 && s != 2 && s != 4) s = 0;
   }
-  return s;
+  return s ? s : (n <= ((size_t)1 << 20) ? 4 : 2);
 }
-// smallest range (elements per stream) worth a stream of its own (ECFFT_B200_ENTER_FORK_MIN = log2, default 19)
+// smallest range (elements per stream) worth a stream of its own (ECFFT_B200_ENTER_FORK_MIN = log2, default 17)
 static size_t enter_fork_min() {
   static size_t v = 0;
   if (!v) {
     const char* e = getenv("ECFFT_B200_ENTER_FORK_MIN");
-    int lg = e ? atoi(e) : 19;
-    if (lg < 10 || lg > 40) lg = 19;
+    int lg = e ? atoi(e) : 17;
+    if (lg < 10 || lg > 40) lg = 17;
     v = (size_t)1 << lg;
   }
   return v;
@@ -113,7 +116,7 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
   if (enter_range_flow(in, out, n, m_lo, m_hi)) return;
   // Independent ranges on concurrent streams: range s runs the depths up to m_mid (the largest block size
   // that tiles a range) on stream s, the caller's stream joins them and runs the remaining depths.
-  const int S = enter_streams();
+  const int S = enter_streams(n);
   if (S > 1 && !prof::enabled() && n % (size_t)S == 0 && n / (size_t)S >= enter_fork_min()) {
     const size_t part = n / (size_t)S;
     size_t m_mid = m_hi;
