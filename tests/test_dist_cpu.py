@@ -174,3 +174,92 @@ def test_enter_sharded_rejects_bad_chunking():
         assert out.shape == (16, 4)
     finally:
         dist.destroy_process_group()
+
+
+# ---- sharded EXIT (csrc/sharded.cu exit_peer): the per-rank bookkeeping, played on CPU over gloo -------------------
+def _exit_worker(rank, world, port, n, result_dir):
+    """Each rank holds evaluations [rank c, (rank+1) c).  Top log2(world) depths: MOD = REDC, x c, REDC
+    (reference src/fftree.rs:232-259, 277-281) on vectors spread over r ranks — every pointwise step works on the
+    rank's chunk with table offsets, the two EXTENDs of a REDC are EXTENDs of the distributed half-length vector
+    (played here by gathering the group's chunks and calling the oracle) — then the split u0 | v0 (src/fftree.rs:
+    206-220) moves half-chunks to their new owners exactly as exit_peer does; below, a local EXIT(c)."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle as O
+        tree = O.OracleTree.build(n)
+        x = O.random_elements(n, seed=17)
+        want = tree.exit(x)
+        c = n // world
+        cc = c // 2
+        cur = _ints(torch.from_numpy(x[rank * c:(rank + 1) * c].view(np.int64).copy()))   # Montgomery values as ints
+        R = 2**256 % P
+        rinv = pow(R, -1, P)
+
+        def mmul(a, b):   # product of two Montgomery-form values, Montgomery form (ark-ff `*`)
+            return a * b * rinv % P
+
+        def gather_group(vals, group0, r):
+            """the r ranks group0 .. group0 + r - 1 each hold `vals`; returns their concatenation"""
+            bufs = [torch.zeros((len(vals), 4), dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(bufs, _tensor(vals))
+            out = []
+            for g in range(group0, group0 + r):
+                out += _ints(bufs[g])
+            return out
+
+        m, r = n, world
+        while r > 1:
+            st = tree.subtree_with_size(m)
+            tab = {name: _ints(torch.from_numpy(st.table(name).view(np.int64))) for name in
+                   ("xnn_s", "xnn_s_inv", "z0_inv_s1", "z0z0_rem_xnn_s")}
+            k, group0 = rank % r, rank - rank % r
+            pos0 = k * cc
+
+            def dist_extend(vals, moiety):
+                full = gather_group(vals, group0, r)
+                arr = _tensor(full).numpy().view(np.uint64)
+                return _ints(torch.from_numpy(st.extend(arr, moiety).view(np.int64)))[pos0:pos0 + cc]
+
+            def redc(ev):   # fftree.rs:232-259 with a = xnn_s on this rank's chunk
+                e0, e1 = ev[0::2], ev[1::2]
+                a = tab["xnn_s"]
+                t0 = [mmul(e0[i], tab["xnn_s_inv"][2 * (pos0 + i)]) for i in range(cc)]
+                g1 = dist_extend(t0, 1)
+                h1 = [mmul((e1[i] - mmul(g1[i], a[2 * (pos0 + i) + 1])) % P, tab["z0_inv_s1"][pos0 + i]) for i in range(cc)]
+                h0 = dist_extend(h1, 0)
+                out = [0] * c
+                out[0::2], out[1::2] = h0, h1
+                return out
+
+            hb = redc(cur)
+            hb = [mmul(hb[j], tab["z0z0_rem_xnn_s"][k * c + j]) for j in range(c)]
+            M = redc(hb)
+            u0 = M[0::2]
+            v0 = [mmul((cur[2 * i] - u0[i]) % P, tab["xnn_s_inv"][2 * (pos0 + i)]) for i in range(cc)]
+            # exchange: rank k' of a half takes its two pieces from ranks 2k', 2k'+1 of the parent group
+            r2 = r // 2
+            newk, second = k % r2, k >= r2
+            src_a, src_b = group0 + 2 * newk, group0 + 2 * newk + 1
+            bufs_u = [torch.zeros((cc, 4), dtype=torch.int64) for _ in range(world)]
+            bufs_v = [torch.zeros((cc, 4), dtype=torch.int64) for _ in range(world)]
+            dist.all_gather(bufs_u, _tensor(u0))
+            dist.all_gather(bufs_v, _tensor(v0))
+            part = bufs_v if second else bufs_u
+            cur = _ints(part[src_a]) + _ints(part[src_b])
+            m //= 2
+            r = r2
+        local = tree.subtree_with_size(c).exit(_tensor(cur).numpy().view(np.uint64))
+        ok = (local == want[rank * c:(rank + 1) * c]).all()
+        np.save(os.path.join(result_dir, f"exit_ok_{rank}.npy"), np.array([ok]))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_exit_sharded_bookkeeping_matches_single_exit(world, tmp_path):
+    n = 64
+    mp.spawn(_exit_worker, args=(world, _free_port(), n, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert np.load(tmp_path / f"exit_ok_{r}.npy")[0]
