@@ -104,6 +104,20 @@ cudaStream_t Tree::aux_stream(int i) const {
   return aux[i];
 }
 
+// ECFFT_B200_FOLD (default 1): between two depths of one ENTER the data is stored already multiplied by the
+// pre-scale of the EXTEND that reads it next.  That EXTEND then skips its pre-scale pass (one product and one
+// reduction per element), the combine that produced the data pays nothing for it (its even output becomes a
+// two-product dot with the scale in the tables, its odd output already was one), and the combine after it
+// divides the scale back out through its own tables: 2.5 -> 2 products and 2 -> 1 reductions per element and
+// depth outside the butterflies.  The first depth of a range reads plain data, the last one writes plain data.
+static bool fold_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_FOLD");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
   // n is any whole number of m_hi-blocks (the blocks are independent): a power of two for a full ENTER
   if (!is_pow2(m_lo) || !is_pow2(m_hi)) throw Error(ERR_NOT_POW2, "length is not a power of two");
@@ -123,19 +137,22 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
     while (m_mid > m_lo && part % m_mid) m_mid /= 2;
     if (m_mid > m_lo) {
       Fp* mid = m_mid == m_hi ? out : tmp(n);
+      // the data handed from the per-range depths to the joint depths stays folded (enter_range_serial)
+      bool keep = m_mid < m_hi && fold_enabled() && k::butterfly_mode() == 2 && getenv("ECFFT_B200_NO_COMBINE_FUSION") == nullptr;
+      for (size_t m = m_lo * 2; keep && m <= m_hi; m *= 2) keep = level_for(m).sym && level_for(m).has_norm();
       ScopedEvent fork, join[3];
       ECFFT_CUDA(cudaEventRecord(fork.e, st));
       for (int s = 1; s < S; s++) {
         cudaStream_t as = t.aux_stream(s - 1);
         ECFFT_CUDA(cudaStreamWaitEvent(as, fork.e, 0));
         Engine sub(t, as);
-        sub.enter_range_serial(in + s * part, mid + s * part, part, m_lo, m_mid);
+        sub.enter_range_serial(in + s * part, mid + s * part, part, m_lo, m_mid, false, keep);
         ECFFT_CUDA(cudaEventRecord(join[s - 1].e, as));
       }
-      enter_range_serial(in, mid, part, m_lo, m_mid);
+      enter_range_serial(in, mid, part, m_lo, m_mid, false, keep);
       for (int s = 1; s < S; s++) ECFFT_CUDA(cudaStreamWaitEvent(st, join[s - 1].e, 0));
       if (m_mid < m_hi) {
-        enter_range_serial(mid, out, n, m_mid, m_hi);
+        enter_range_serial(mid, out, n, m_mid, m_hi, keep, false);
         release(mid);
       }
       return;
@@ -196,11 +213,44 @@ bool Engine::enter_range_flow(const Fp* in, Fp* out, size_t n, size_t m_lo, size
   return true;
 }
 
-void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
+bool Engine::fold_tabs(const Level& lv, int group) const {
+  const uint32_t k = lv.log_n;
+  if (k < 1 || !(lv.sym && lv.has_norm())) return false;
+  const bool needs_next = group != 2;
+  if (needs_next && (k + 1 > t.log_n || !t.levels[k + 1].gami[0])) return false;
+  std::lock_guard<std::mutex> lock(t.tab_mu);
+  if (lv.fold_tab[2 * group + 1]) return true;
+  const size_t h = (size_t)1 << (k - 1);
+  cudaStream_t bs = t.stream;
+  Fp* tab[2];
+  for (int i = 0; i < 2; i++) {
+    void* p = nullptr;
+    ECFFT_CUDA(cudaMallocAsync(&p, h * sizeof(Fp), bs));   // stream-ordered, see exit_tabs
+    t.owned_lazy.push_back(p);
+    tab[i] = (Fp*)p;
+  }
+  Fp two_pow_L = fp_zero();   // 1 / gami[0][i] = gam[0][i] 2^(k-1) (build_norm_tables)
+  two_pow_L.v[(k - 1) / 32] = 1u << ((k - 1) % 32);
+  k::fold_tables(group, tab[0], tab[1], lv.gam[0], lv.gam[1], lv.gx, lv.xnn_s, needs_next ? t.levels[k + 1].gami[0] : nullptr, two_pow_L, h, bs);
+  ECFFT_CUDA(cudaStreamSynchronize(bs));
+  lv.fold_tab[2 * group] = tab[0];
+  lv.fold_tab[2 * group + 1] = tab[1];
+  return true;
+}
+
+void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, bool in_folded, bool out_folded) const {
   if (m_lo == m_hi) {
+    if (in_folded != out_folded) throw Error(ERR_INVALID_ARG, "enter: an empty range cannot change the folding");
     if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, n * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
     return;
   }
+  // folding needs the symmetric tables on every depth of the range (and the level above a folded output)
+  bool fold = fold_enabled() && k::butterfly_mode() == 2 && getenv("ECFFT_B200_NO_COMBINE_FUSION") == nullptr;
+  for (size_t m = m_lo * 2; fold && m <= m_hi; m *= 2) {
+    const Level& lv = level_for(m);
+    fold = lv.sym && lv.has_norm();
+  }
+  if (!fold && (in_folded || out_folded)) throw Error(ERR_INVALID_ARG, "enter: folded data needs the symmetric tables");
   Fp* W = tmp(n);
   Fp* ping[2] = {nullptr, nullptr};
   const Fp* cur = in;
@@ -220,11 +270,35 @@ void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, si
     const bool unscaled = k::butterfly_mode() != 0 && lv.has_norm();
     static const bool no_fuse = getenv("ECFFT_B200_NO_COMBINE_FUSION") != nullptr;
     if (unscaled && lv.sym && !no_fuse) {  // EXTEND with the combine fused into its last pass
-      k::SymCombine c{cur, lv.xnn_s, lv.gam[1], lv.gx, dst};
-      if (k::extend_sym(lv.tw_d[0], lv.tw_r[1], lv.ctr[1], cur, W, ilog2(h), n / h, lv.gami[0], nullptr, &c, st)) {
-        cur = dst;
-        continue;
+      bool fin = fold && (m == m_lo * 2 ? in_folded : true);
+      bool fout = fold && (m == m_hi ? out_folded : true);
+      if (fout && !fold_tabs(lv, 0)) throw Error(ERR_INVALID_ARG, "enter: no level above to fold for");
+      if (fin && fout && !fold_tabs(lv, 1)) throw Error(ERR_INVALID_ARG, "enter: fold tables");
+      if (fin && !fout && !fold_tabs(lv, 2)) throw Error(ERR_INVALID_ARG, "enter: fold tables");
+      if (!fin && fout && !fold_tabs(lv, 3)) throw Error(ERR_INVALID_ARG, "enter: fold tables");
+      k::SymCombine c{cur, lv.xnn_s, fout ? lv.fold_tab[0] : lv.gam[1], fout ? lv.fold_tab[1] : lv.gx, dst};
+      if (fin || fout) {
+        const int g = fin && fout ? 1 : (fin ? 2 : 3);
+        c.e0 = lv.fold_tab[2 * g];
+        c.e1 = lv.fold_tab[2 * g + 1];
       }
+      const Fp* pre = fin ? nullptr : lv.gami[0];
+      const uint32_t log_h = ilog2(h);
+      if (!k::extend_sym(lv.tw_d[0], lv.tw_r[1], lv.ctr[1], cur, W, log_h, n / h, pre, nullptr, &c, st)) {
+        // depths the fused pass does not take (h = 1: EXTEND is the identity, fftree.rs:74-76; h = tile: no room for
+        // the sibling vector): unscaled EXTEND into W, then the combine as a pass of its own
+        const Fp* Wsrc = cur;   // h = 1: both scales of the 2-leaf level are 1
+        if (h > 1) {
+          if (!k::extend_sym(lv.tw_d[0], lv.tw_r[1], lv.ctr[1], cur, W, log_h, n / h, pre, nullptr, nullptr, st)) {
+            k::extend(lv, cur, W, log_h, n / h, S1, st, true);   // fewer than 4 elements: the radix-2 kernel (applies the pre-scale itself)
+            if (fin) throw Error(ERR_INVALID_ARG, "enter: EXTEND refused a depth it should take");
+          }
+          Wsrc = W;
+        }
+        k::enter_combine_tabs(c, Wsrc, log_h, n, st);
+      }
+      cur = dst;
+      continue;
     }
     k::extend(lv, cur, W, ilog2(h), n / h, S1, st, unscaled);
     k::enter_combine(lv, cur, W, dst, ilog2(h), n, unscaled, st);

@@ -108,6 +108,13 @@ struct Level {
   // tables (kernels.cu redc_tables) depend on the level only and are built once, on first use (Engine::exit_tabs)
   mutable Fp* exit_tab[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [redc 0 | redc 1 (x c)][P1, Kp, Zc], h each
   mutable Fp* exit_a0inv = nullptr;   // xnn_s_inv[::2], h
+  // ENTER with the next depth's pre-scale folded into this depth's combine (Engine::fold_tabs; built on first use, h each).
+  // P = gami[0] of this level (the scale its input carries when "folded"), Pn = gami[0] of the level above (the scale
+  // its output is to carry):  [0] gam[1][i] Pn[2i+1], [1] gx[i] Pn[2i+1]              (odd outputs, folded out)
+  //   [2] Pn[2i] / P[i],  [3] xnn[2i] Pn[2i] / P[i]   (even outputs, folded in and out)
+  //   [4] 1 / P[i],       [5] xnn[2i] / P[i]          (folded in, plain out)
+  //   [6] Pn[2i],         [7] xnn[2i] Pn[2i]          (plain in, folded out)
+  mutable Fp* fold_tab[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool has_norm() const { return tw_r[0] && tw_r[1] && tw_d[0] && tw_d[1] && gam[0] && gam[1] && gami[0] && gami[1] && gx; }
 };
 
@@ -167,7 +174,8 @@ void extend_sub(const Level& lv, const Fp* in, Fp* out, uint32_t log_len, cudaSt
 // (fftree.rs:155-159) into the last pass: vectors 2w, 2w+1 are u, v of block w, comb->A the depth's
 // unscaled input, and the result goes to comb->out.  Returns false when it does not apply (fewer than 4
 // elements; a depth whose vector length equals the tile cannot take the fused combine).
-struct SymCombine { const Fp* A; const Fp* xnn; const Fp* gam; const Fp* gx; Fp* out; };
+// e0 != null: the even output is e0[i] u0 + e1[i] v0 (one reduction) instead of u0 + v0 xnn[2i] — the folded forms.
+struct SymCombine { const Fp* A; const Fp* xnn; const Fp* gam; const Fp* gx; Fp* out; const Fp* e0 = nullptr; const Fp* e1 = nullptr; };
 // One pass of k_extend_sym (a launch of the per-pass kernel, or one entry of a flow: sym_kernel.cu)
 struct SymParams {
   const Fp* in;
@@ -181,6 +189,8 @@ struct SymParams {
   const Fp* xnn;
   const Fp* gam;
   const Fp* gx;
+  const Fp* ce0;    // combine epilogue, folded forms: even output = ce0[i] u0 + ce1[i] v0 (null: u0 + v0 xnn[2i])
+  const Fp* ce1;
   unsigned long long nv;      // strided: vectors (pair: vector pairs) in the batch; blocks are ordered batch-major
   unsigned long long total;   // elements in the batch (guards the ragged tile of tiny inputs)
   uint32_t log_h, log_t;
@@ -200,6 +210,8 @@ struct SymParams {
   // split != 0 (EXIT's last EXTEND of a depth, src/fftree.rs:206-220): u0 = x * post is stored at
   // out[(vector << (log_h + 1)) + i] and v0 = (E[(g << e_shift) + e_off] - u0) * Z[i] at the same place + h
   uint32_t split;
+  uint32_t tma_fence;
+  uint32_t pf;                // twiddle prefetch ahead of each stage: 0 off, 1 into L1, 2 into L2 (set by launch_sym)
   // ---- flow fields (k_sym_flow: all passes of an ENTER in one persistent launch) ----
   uint32_t kind;              // 0: butterfly tile pass; 1: combine-only pass (in = [u1 | v1] unscaled, A = [u0 | v0])
   uint32_t tile_begin, ntiles;         // this pass's range of the flow's tile queue
@@ -242,6 +254,9 @@ int butterfly_mode();  // ECFFT_B200_BUTTERFLY: 2 = symmetric (default), 1 = nor
 // ENTER combine, fftree.rs:155-159, batched over n/(2h) blocks.  W_unscaled: W lacks the Gamma^1
 // scaling (lv.gam[1], lv.gx are used instead of xnn's odd entries).
 void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t log_h, size_t n, bool W_unscaled, cudaStream_t st);
+void enter_combine_tabs(const SymCombine& c, const Fp* W, uint32_t log_h, size_t n, cudaStream_t st);  // W unscaled; any table set
+// the folded-combine tables of Level::fold_tab: group 0 = [0],[1]; 1 = [2],[3]; 2 = [4],[5]; 3 = [6],[7]
+void fold_tables(int group, Fp* t0, Fp* t1, const Fp* gam0, const Fp* gam1, const Fp* gx, const Fp* xnn, const Fp* Pn, Fp two_pow_L, size_t h, cudaStream_t st);
 
 void mul_const(Fp* out, const Fp* in, Fp c, size_t n, cudaStream_t st);                       // out = in*c
 void mul_bcast(Fp* out, const Fp* in, const Fp* c, size_t len, size_t nvec, cudaStream_t st); // out[v][i] = in[v][i]*c[i]
@@ -310,7 +325,10 @@ struct Engine {
 
   // the FFTree<F> surface (fftree.rs:72-316) on device buffers
   void enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // bottom-up levels m_lo < m <= m_hi
-  void enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // ... on this engine's stream only
+  // ... on this engine's stream only.  in_folded / out_folded: the input already carries / the output is to carry the
+  // pre-scale of the EXTEND that consumes it next (the data between two depths of one ENTER)
+  void enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, bool in_folded = false, bool out_folded = false) const;
+  bool fold_tabs(const Level& lv, int group) const;  // builds lv.fold_tab[2 group], [2 group + 1] once
   bool enter_range_flow(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;    // ... as one flow launch (false: not applicable)
   void enter(const Fp* coeffs, Fp* out, size_t n) const { enter_range(coeffs, out, n, 1, n); }
   void exit(const Fp* evals, Fp* out, size_t n) const;

@@ -132,6 +132,63 @@ void enter_combine(const Level& lv, const Fp* A, const Fp* W, Fp* out, uint32_t 
   ECFFT_CUDA(cudaGetLastError());
 }
 
+// the same pass for any table set of the unscaled form (the folded combines of Engine::enter_range_serial)
+__global__ void __launch_bounds__(256) k_enter_combine_tabs(const Fp* __restrict__ A, const Fp* __restrict__ W, const Fp* __restrict__ xnn,
+                                                            const Fp* __restrict__ e0, const Fp* __restrict__ e1, const Fp* __restrict__ o0,
+                                                            const Fp* __restrict__ o1, Fp* __restrict__ out, uint32_t log_h, unsigned long long npairs) {
+  for (unsigned long long idx = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; idx < npairs;
+       idx += (unsigned long long)gridDim.x * blockDim.x) {
+    const unsigned long long blk = idx >> log_h, i = idx & ((1ull << log_h) - 1), off = blk << (log_h + 1), h = 1ull << log_h;
+    const Fp u0 = fp_load(A + off + i), v0 = fp_load(A + off + h + i);
+    const Fp r0 = e0 ? fp_dot2_lazy(fp_load_ro(e0 + i), u0, fp_load_ro(e1 + i), v0) : fp_muladd_lazy(u0, v0, fp_load_ro(xnn + 2 * i));
+    fp_store(out + off + 2 * i, fp_canon(r0));
+    const Fp u1 = fp_load(W + off + i), v1 = fp_load(W + off + h + i);
+    fp_store(out + off + 2 * i + 1, fp_canon(fp_dot2_lazy(fp_load_ro(o0 + i), u1, fp_load_ro(o1 + i), v1)));
+  }
+}
+void enter_combine_tabs(const SymCombine& c, const Fp* W, uint32_t log_h, size_t n, cudaStream_t st) {
+  const size_t npairs = n / 2;
+  unsigned grid = (unsigned)((npairs + 255) / 256);
+  if (grid > 148u * 32u) grid = 148u * 32u;
+  const bool timed = prof::enabled();
+  if (timed) prof::record_begin(prof::ENTER_COMBINE, 128.0 * (double)n, st);
+  k_enter_combine_tabs<<<grid, 256, 0, st>>>(c.A, W, c.xnn, c.e0, c.e1, c.gam, c.gx, c.out, log_h, npairs);
+  if (timed) prof::record_end(st);
+  prof::count_launch();
+  ECFFT_CUDA(cudaGetLastError());
+}
+void fold_tables(int group, Fp* t0, Fp* t1, const Fp* gam0, const Fp* gam1, const Fp* gx, const Fp* xnn, const Fp* Pn, Fp two_pow_L, size_t h, cudaStream_t st) {
+  switch (group) {
+    case 0:  // odd outputs, folded out
+      map(h, st, [=] __device__(size_t i) {
+        const Fp s = fp_load_ro(Pn + 2 * i + 1);
+        fp_store(t0 + i, fp_mul(fp_load_ro(gam1 + i), s));
+        fp_store(t1 + i, fp_mul(fp_load_ro(gx + i), s));
+      });
+      break;
+    case 1:  // even outputs, folded in and out: 1 / P[i] = gam0[i] 2^L
+      map(h, st, [=] __device__(size_t i) {
+        const Fp s = fp_mul(fp_mul_lazy(fp_load_ro(gam0 + i), two_pow_L), fp_load_ro(Pn + 2 * i));
+        fp_store(t0 + i, s);
+        fp_store(t1 + i, fp_mul(fp_load_ro(xnn + 2 * i), s));
+      });
+      break;
+    case 2:  // folded in, plain out
+      map(h, st, [=] __device__(size_t i) {
+        const Fp s = fp_mul(fp_load_ro(gam0 + i), two_pow_L);
+        fp_store(t0 + i, s);
+        fp_store(t1 + i, fp_mul(fp_load_ro(xnn + 2 * i), s));
+      });
+      break;
+    default:  // plain in, folded out
+      map(h, st, [=] __device__(size_t i) {
+        const Fp s = fp_load_ro(Pn + 2 * i);
+        fp_store(t0 + i, s);
+        fp_store(t1 + i, fp_mul(fp_load_ro(xnn + 2 * i), s));
+      });
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // pointwise glue
 // ------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@
 // for which a tile holds the same positions of the two sibling vectors u and v.  The first load and the
 // last store can be stride-2 views and the store can add a second operand (e1 * Z + x * post), which is
 // how REDC's de-interleave, pointwise steps and interleave (src/fftree.rs:232-259) ride the two EXTENDs.
+#include <cuda.h>   // CUtensorMap and the cuTensorMapEncodeTiled prototype only: the entry point is looked up at run time
 #include <cstdlib>
 
 #include "engine.h"
@@ -67,6 +68,34 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
 
+// ---- TMA tile load (ECFFT_B200_TMA=1): the tile arrives as bulk tensor copies issued by ONE thread and
+// completes on an mbarrier, instead of 16 cp.async per thread.  The buffer is seen as a 3-D tensor of u32:
+// [row = element >> row_shift][column = element & (2^row_shift - 1)][8 limbs]; a box of {4 limbs, <= 256 columns,
+// 2^krows rows} lands densely in shared memory, which is exactly one half (low or high 16 bytes) of the split
+// tile layout.  Elements beyond the batch are zero-filled by the copy engine.
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra WAIT_%=;\n\t}"
+      ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, int c0, int c1, int c2, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+               ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
+                 "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 // tile element -> (offset from the tile's first global element, position within its vector)
 struct TileMap {
   uint32_t log_c, cmask, rmask, krows, row_shift, log_h, pos0;
@@ -78,12 +107,101 @@ struct TileMap {
   }
 };
 
+// One stage of a tile: the quad of item q differs in tile-index bits b_lo (level jl) and b_hi (level jh); ops
+// selects which of the level operations run.  When both levels are used jl = jh - 1, so the two low-level pairs
+// share a twiddle.  Single-level stages (odd level counts) pair bit b_hi only; b_lo is any other bit.
+struct Stage {
+  uint32_t ops, jh, jl, b1, b2, S_lo, S_hi, mh, ml;
+};
+struct StagePlan {
+  uint32_t nD, mid, j_base, odd, npairs, nstages;
+  __device__ __forceinline__ StagePlan(const SymParams& p) {
+    const uint32_t nlev = p.lvl_hi - p.lvl_lo;
+    mid = (p.do_d && p.do_r && nlev >= 2) ? 1u : 0u;   // levels lvl_lo+1, lvl_lo run D, D+R (one product), R in one stage
+    j_base = p.lvl_lo + (mid ? 2 : 0);                 // lowest level of the plain D / R stages
+    const uint32_t cnt = p.lvl_hi - j_base;
+    odd = cnt & 1;
+    npairs = cnt >> 1;
+    nD = p.do_d ? odd + npairs : 0;
+    const uint32_t nR = p.do_r ? odd + npairs : 0;
+    nstages = nD + mid + nR;
+  }
+  __device__ __forceinline__ Stage stage(const SymParams& p, uint32_t sidx) const {
+    Stage g;
+    if (sidx < nD) {
+      if (odd && sidx == 0) { g.ops = OP_D_HI; g.jh = p.lvl_hi - 1; g.jl = 0; }
+      else { const uint32_t u = sidx - odd; g.ops = OP_D_HI | OP_D_LO; g.jh = p.lvl_hi - 1 - odd - 2 * u; g.jl = g.jh - 1; }
+    } else if (mid && sidx == nD) {
+      g.ops = OP_D_HI | OP_C_LO | OP_R_HI; g.jh = p.lvl_lo + 1; g.jl = p.lvl_lo;
+    } else {
+      const uint32_t t = sidx - nD - mid;
+      if (t < npairs) { g.ops = OP_R_LO | OP_R_HI; g.jl = j_base + 2 * t; g.jh = g.jl + 1; }
+      else { g.ops = OP_R_HI; g.jh = p.lvl_hi - 1; g.jl = 0; }
+    }
+    const bool two = (g.ops & (OP_D_LO | OP_R_LO | OP_C_LO)) != 0;
+    const uint32_t b_hi = g.jh + p.boff;
+    const uint32_t b_lo = two ? g.jl + p.boff : (b_hi == 0 ? 1u : b_hi - 1);
+    g.b1 = b_lo < b_hi ? b_lo : b_hi;
+    g.b2 = b_lo < b_hi ? b_hi : b_lo;
+    g.S_lo = 1u << b_lo;
+    g.S_hi = 1u << b_hi;
+    g.mh = (1u << g.jh) - 1;
+    g.ml = (1u << g.jl) - 1;
+    return g;
+  }
+};
+__device__ __forceinline__ uint32_t quad_e0(uint32_t q, const Stage& g) {
+  uint32_t e0 = ((q >> g.b1) << (g.b1 + 1)) | (q & ((1u << g.b1) - 1));   // zero bit at b1
+  return ((e0 >> g.b2) << (g.b2 + 1)) | (e0 & ((1u << g.b2) - 1));        // and at b2
+}
+
+// Twiddle prefetch (ECFFT_B200_TW_PREFETCH = 1: into L1, 2: into L2): while a stage computes, the lines the NEXT
+// stage's butterflies of this thread will load through the read-only path are requested, so the per-butterfly
+// twiddle loads of the strided passes (one 32-byte value per butterfly, no reuse inside a tile) stop
+// exposing the L2 / DRAM latency.  Levels with small tables (< 256 twiddles) stay cached anyway and are skipped.
+template <int NT>
+__device__ __forceinline__ void prefetch_stage(const SymParams& p, const TileMap& tm, const Stage& g, uint32_t T, bool first) {
+  const uint32_t hmask = (1u << p.log_h) - 1;
+  const bool hi_big = g.jh >= 8, lo_big = g.jl >= 8;
+  if (!hi_big && !lo_big && !first) return;
+#pragma unroll 1
+  for (uint32_t q = threadIdx.x; q < T / 4; q += NT) {
+    const uint32_t e0 = quad_e0(q, g), e1 = e0 + g.S_lo;
+    unsigned long long g0;
+    uint32_t pa, pb;
+    tm.map(e0, g0, pa);
+    tm.map(e1, g0, pb);
+    const Fp *t0 = nullptr, *t1 = nullptr, *t2 = nullptr;
+    if (hi_big) {
+      const Fp* tab = (g.ops & OP_D_HI) && !(g.ops & OP_R_HI) ? p.tw_d : p.tw_r;   // the centre stage loads both: its levels are tiny
+      t0 = tab + (1u << g.jh) + (pa & g.mh);
+      t1 = tab + (1u << g.jh) + (pb & g.mh);
+    }
+    if (lo_big && (g.ops & (OP_D_LO | OP_R_LO))) t2 = ((g.ops & OP_D_LO) ? p.tw_d : p.tw_r) + (1u << g.jl) + (pa & g.ml);
+    if (p.pf == 1) {
+      if (t0) { prefetch_l1(t0); prefetch_l1(t1); }
+      if (t2) prefetch_l1(t2);
+    } else {
+      if (t0) { prefetch_l2(t0); prefetch_l2(t1); }
+      if (t2) prefetch_l2(t2);
+    }
+    if (first) {   // the pre-scale table of the first stage: positions of the whole quad
+      uint32_t pc, pd;
+      tm.map(e0 + g.S_hi, g0, pc);
+      tm.map(e1 + g.S_hi, g0, pd);
+      prefetch_l1(p.pre + (pa & hmask)); prefetch_l1(p.pre + (pb & hmask));
+      prefetch_l1(p.pre + (pc & hmask)); prefetch_l1(p.pre + (pd & hmask));
+    }
+  }
+}
+
 // One tile of one pass.  Packed tiles start at element gbase_packed; strided tiles are tile `tile` of vector
 // (pair) w.  FLOW: the data buffers may have been written by other CTAs of the SAME launch, so every read of
-// them goes to L2 (cp.async.cg, ld.global.cg), never through L1.
-template <int NT, bool FLOW>
+// them goes to L2 (cp.async.cg, ld.global.cg), never through L1.  TMA: the tile load is a bulk tensor copy.
+template <int NT, bool FLOW, bool TMA>
 __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, unsigned long long w, unsigned long long tile,
-                                         unsigned long long gbase_packed) {
+                                         unsigned long long gbase_packed, const CUtensorMap* tmap = nullptr,
+                                         unsigned long long* mbar = nullptr) {
   const uint32_t T = 1u << p.log_t;
   const TileSoA s{smem_raw, T};
   const uint32_t hmask = (1u << p.log_h) - 1;
@@ -100,63 +218,65 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
     tm = TileMap{p.log_c, (1u << p.log_c) - 1, (1u << p.krows) - 1, p.krows, p.row_shift, p.log_h, pos0};
     gbase = ((p.pair ? 2 * w : w) << p.log_h) + pos0;
   }
+  const StagePlan plan(p);
+  Stage cur = plan.stage(p, 0);
 
-  // ---- tile load: cp.async straight into the split shared-memory layout
-  for (uint32_t e = threadIdx.x; e < T; e += NT) {
-    unsigned long long goff;
-    uint32_t pos;
-    tm.map(e, goff, pos);
-    const unsigned long long g = gbase + goff;
-    if (g < p.total) {
-      const uint4* src = reinterpret_cast<const uint4*>(p.in + ((g << p.in_shift) + p.in_off));
-      cp_async16(&s.s[e], src);
-      cp_async16(&s.s[T + e], src + 1);
-    } else {
-      s.st(e, fp_zero());
+  // ---- tile load
+  if (TMA) {
+    // one thread: arm the barrier with the tile's bytes, issue the boxes (low halves, then high halves)
+    if (threadIdx.x == 0) {
+      const uint32_t rs = p.packed ? p.log_t : p.row_shift;           // the tensor map's row length is 2^rs elements
+      const uint32_t lc = p.packed ? p.log_t : p.log_c, kr = p.packed ? 0u : p.krows;
+      const uint32_t bc_log = lc < 8 ? lc : 8;                        // box: 2^bc_log columns x 2^kr rows
+      const uint32_t nchunk = 1u << (lc - bc_log), npair = p.pair ? 2u : 1u;
+      const int c1 = (int)(gbase & ((1ull << rs) - 1)), c2 = (int)(gbase >> rs);
+      if (p.tma_fence) asm volatile("fence.proxy.async;" ::: "memory");   // debugging aid (ECFFT_B200_TMA=2)
+      mbar_expect_tx(mbar, T * (uint32_t)sizeof(Fp));
+      for (uint32_t hf = 0; hf < 2; hf++)
+        for (uint32_t pb = 0; pb < npair; pb++)
+          for (uint32_t cc = 0; cc < nchunk; cc++)
+            tma_load_3d(&s.s[hf * T + (pb << (kr + lc)) + (cc << bc_log)], tmap, (int)(hf * 4), c1 + (int)(cc << bc_log),
+                        c2 + (int)(pb << (p.log_h - rs)), mbar);
     }
+    if (p.pf) prefetch_stage<NT>(p, tm, cur, T, p.pre != nullptr);
+    mbar_wait(mbar, 0);
+  } else {
+    // cp.async straight into the split shared-memory layout
+    for (uint32_t e = threadIdx.x; e < T; e += NT) {
+      unsigned long long goff;
+      uint32_t pos;
+      tm.map(e, goff, pos);
+      const unsigned long long g = gbase + goff;
+      if (g < p.total) {
+        const uint4* src = reinterpret_cast<const uint4*>(p.in + ((g << p.in_shift) + p.in_off));
+        cp_async16(&s.s[e], src);
+        cp_async16(&s.s[T + e], src + 1);
+      } else {
+        s.st(e, fp_zero());
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (p.pf) prefetch_stage<NT>(p, tm, cur, T, p.pre != nullptr);
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
   }
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  __syncthreads();
 
-  // ---- stage schedule (see the header comment of quad stages below)
-  const uint32_t nlev = p.lvl_hi - p.lvl_lo;
-  const bool mid = p.do_d && p.do_r && nlev >= 2;       // levels lvl_lo+1, lvl_lo run D, D+R (one product), R in one stage
-  const uint32_t j_base = p.lvl_lo + (mid ? 2 : 0);     // lowest level of the plain D / R stages
-  const uint32_t cnt = p.lvl_hi - j_base, odd = cnt & 1, npairs = cnt >> 1;
-  const uint32_t nD = p.do_d ? odd + npairs : 0, nR = p.do_r ? odd + npairs : 0;
-  const uint32_t nstages = nD + (mid ? 1 : 0) + nR;
-
-  for (uint32_t sidx = 0; sidx < nstages; sidx++) {
-    // The quad of item q differs in tile-index bits b_lo (level jl) and b_hi (level jh); ops selects which
-    // of the level operations run.  When both levels are used jl = jh - 1, so the two low-level pairs
-    // share a twiddle.  Single-level stages (odd level counts) pair bit b_hi only; b_lo is any other bit.
-    uint32_t ops, jh, jl;
-    if (sidx < nD) {
-      if (odd && sidx == 0) { ops = OP_D_HI; jh = p.lvl_hi - 1; jl = 0; }
-      else { const uint32_t u = sidx - odd; ops = OP_D_HI | OP_D_LO; jh = p.lvl_hi - 1 - odd - 2 * u; jl = jh - 1; }
-    } else if (mid && sidx == nD) {
-      ops = OP_D_HI | OP_C_LO | OP_R_HI; jh = p.lvl_lo + 1; jl = p.lvl_lo;
-    } else {
-      const uint32_t t = sidx - nD - (mid ? 1 : 0);
-      if (t < npairs) { ops = OP_R_LO | OP_R_HI; jl = j_base + 2 * t; jh = jl + 1; }
-      else { ops = OP_R_HI; jh = p.lvl_hi - 1; jl = 0; }
+  // ---- stages
+  for (uint32_t sidx = 0; sidx < plan.nstages; sidx++) {
+    const Stage g = cur;
+    if (sidx + 1 < plan.nstages) {
+      cur = plan.stage(p, sidx + 1);
+      if (p.pf) prefetch_stage<NT>(p, tm, cur, T, false);
     }
-    const bool two = (ops & (OP_D_LO | OP_R_LO | OP_C_LO)) != 0;
-    const uint32_t b_hi = jh + p.boff;
-    const uint32_t b_lo = two ? jl + p.boff : (b_hi == 0 ? 1u : b_hi - 1);
-    const uint32_t b1 = b_lo < b_hi ? b_lo : b_hi, b2 = b_lo < b_hi ? b_hi : b_lo;
-    const uint32_t S_lo = 1u << b_lo, S_hi = 1u << b_hi;
-    const uint32_t mh = (1u << jh) - 1, ml = (1u << jl) - 1;
+    const uint32_t ops = g.ops, S_lo = g.S_lo, S_hi = g.S_hi, mh = g.mh, ml = g.ml;
     const bool first = sidx == 0 && p.pre != nullptr;
-    const Fp* d_hi = p.tw_d + (1u << jh);
-    const Fp* d_lo = p.tw_d + (1u << jl);
-    const Fp* r_hi = p.tw_r + (1u << jh);
-    const Fp* r_lo = p.tw_r + (1u << jl);
+    const Fp* d_hi = p.tw_d + (1u << g.jh);
+    const Fp* d_lo = p.tw_d + (1u << g.jl);
+    const Fp* r_hi = p.tw_r + (1u << g.jh);
+    const Fp* r_lo = p.tw_r + (1u << g.jl);
 #pragma unroll 1
     for (uint32_t q = threadIdx.x; q < T / 4; q += NT) {
-      uint32_t e0 = ((q >> b1) << (b1 + 1)) | (q & ((1u << b1) - 1));     // zero bit at b1
-      e0 = ((e0 >> b2) << (b2 + 1)) | (e0 & ((1u << b2) - 1));            // and at b2
+      const uint32_t e0 = quad_e0(q, g);
       const uint32_t e1 = e0 + S_lo, e2 = e0 + S_hi, e3 = e1 + S_hi;
       unsigned long long g0, g1, g2, g3;
       uint32_t pa, pb, pc, pd;
@@ -186,9 +306,9 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
         sym_c_pair(x2, x3, c_lo);
       }
       if (ops & OP_R_LO) {
-        const Fp g = fp_load_ro(r_lo + (pa & ml));
-        sym_r_pair(x0, x1, g);
-        sym_r_pair(x2, x3, g);
+        const Fp gg = fp_load_ro(r_lo + (pa & ml));
+        sym_r_pair(x0, x1, gg);
+        sym_r_pair(x2, x3, gg);
       }
       if (ops & OP_R_HI) {
         sym_r_pair(x0, x2, fp_load_ro(r_hi + (pa & mh)));
@@ -244,7 +364,10 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
       const uint32_t i = pu & hmask;
       Fp* o = p.out + (gu - i) + 2ull * i;
       const Fp u0 = FLOW ? fp_load_cg(p.A + gu) : fp_load(p.A + gu), v0 = FLOW ? fp_load_cg(p.A + gv) : fp_load(p.A + gv);
-      fp_store(o, fp_canon(fp_muladd_lazy(u0, v0, fp_load_ro(p.xnn + 2 * i))));
+      if (p.ce0)   // folded forms: the scale the next depth's EXTEND wants (and / or the one this depth's input carries) in the tables
+        fp_store(o, fp_canon(fp_dot2_lazy(fp_load_ro(p.ce0 + i), u0, fp_load_ro(p.ce1 + i), v0)));
+      else
+        fp_store(o, fp_canon(fp_muladd_lazy(u0, v0, fp_load_ro(p.xnn + 2 * i))));
       const Fp u1 = s.ld(eu), v1 = s.ld(ev);
       fp_store(o + 1, fp_canon(fp_dot2_lazy(fp_load_ro(p.gam + i), u1, fp_load_ro(p.gx + i), v1)));
     }
@@ -253,16 +376,30 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
 
 template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__ SymParams p) {
-  extern __shared__ uint4 smem_raw[];
+  extern __shared__ __align__(128) uint4 smem_raw[];
   // Programmatic dependent launch (ECFFT_B200_PDL=1): the next pass's CTAs may be scheduled while this grid
   // drains — everything below still waits for the previous grid's results (griddepcontrol.wait returns once
   // the prerequisite grid has completed and its memory is visible).  No-ops without the launch attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   if (p.packed)
-    sym_tile<NT, false>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t);
+    sym_tile<NT, false, false>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t);
   else
-    sym_tile<NT, false>(p, smem_raw, blockIdx.x % p.nv, blockIdx.x / p.nv, 0);
+    sym_tile<NT, false, false>(p, smem_raw, blockIdx.x % p.nv, blockIdx.x / p.nv, 0);
+}
+// The same pass with the tile load done by the TMA unit (tensor map encoded per launch by launch_sym)
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB) k_extend_sym_tma(const __grid_constant__ SymParams p, const __grid_constant__ CUtensorMap tmap) {
+  extern __shared__ __align__(128) uint4 smem_raw[];
+  __shared__ __align__(8) unsigned long long mbar;
+  if (threadIdx.x == 0) mbar_init(&mbar, 1);
+  __syncthreads();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.packed)
+    sym_tile<NT, false, true>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t, &tmap, &mbar);
+  else
+    sym_tile<NT, false, true>(p, smem_raw, blockIdx.x % p.nv, blockIdx.x / p.nv, 0, &tmap, &mbar);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -359,7 +496,7 @@ __global__ void __launch_bounds__(NT, MINB) k_sym_flow(const __grid_constant__ F
     }
     if (d.stats && threadIdx.x == 0) s_acc[1] -= clock64();
     if (p.kind == 0) {
-      sym_tile<NT, true>(p, smem_raw, w, t_v, gbase_packed);
+      sym_tile<NT, true, false>(p, smem_raw, w, t_v, gbase_packed);
     } else {
       // combine-only pass (src/fftree.rs:155-159): outputs [first_out, first_out + T) of the batch
       const uint32_t T = 1u << p.log_t;
@@ -425,25 +562,85 @@ static bool pdl_enabled() {
   }
   return v != 0;
 }
+// ECFFT_B200_TMA (default 0): tile loads as cp.async.bulk.tensor copies completing on an mbarrier
+static int tma_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_TMA");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+// ECFFT_B200_TW_PREFETCH: 0 = off, 1 = next stage's twiddles into L1, 2 = into L2
+static uint32_t tw_prefetch_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_TW_PREFETCH");
+    v = e ? atoi(e) : 0;
+    if (v < 0 || v > 2) v = 0;
+  }
+  return (uint32_t)v;
+}
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qr) != cudaSuccess || qr != cudaDriverEntryPointSuccess) f = nullptr;
+    return (EncodeTiledFn)f;
+  }();
+  return fn;
+}
+// Tensor map of a pass's input: [total >> rs][2^rs][8 x u32], box {4, 2^min(log_c, 8), 2^krows}; false when the pass
+// does not have that shape (strided REDC views, batches that are not whole rows): the caller keeps cp.async.
+static bool make_tile_map(const SymParams& p, CUtensorMap* map) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc || p.in_shift || p.in_off || p.kind != 0) return false;
+  const uint32_t rs = p.packed ? p.log_t : p.row_shift;
+  const uint32_t lc = p.packed ? p.log_t : p.log_c, kr = p.packed ? 0u : p.krows;
+  if (p.log_t < 9) return false;   // shared-memory box addresses must be 128-byte aligned; tiny tiles keep cp.async
+  if (p.total < ((unsigned long long)1 << p.log_t) || (p.total & (((unsigned long long)1 << rs) - 1))) return false;
+  if ((reinterpret_cast<uintptr_t>(p.in) & 15) || rs > 26) return false;
+  const uint32_t bc_log = lc < 8 ? lc : 8;
+  const cuuint64_t dims[3] = {8, (cuuint64_t)1 << rs, (cuuint64_t)(p.total >> rs)};
+  const cuuint64_t strides[2] = {sizeof(Fp), (cuuint64_t)sizeof(Fp) << rs};   // bytes, dimensions 1 and 2
+  const cuuint32_t box[3] = {4, 1u << bc_log, 1u << kr};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<Fp*>(p.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <class... Args>
+static void launch_kernel(void (*kern)(Args...), size_t tiles, int nt, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)tiles);
+  cfg.blockDim = dim3(nt);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ECFFT_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
+}
 template <int NT, int MINB>
 static void launch_shape(const SymParams& p, size_t tiles, cudaStream_t st) {
   static PerDeviceOnce configured;
-  configured.run([] { ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp)))); });
-  if (pdl_enabled()) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)tiles);
-    cfg.blockDim = dim3(NT);
-    cfg.dynamicSmemBytes = ((size_t)sizeof(Fp)) << p.log_t;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k_extend_sym<NT, MINB>, p));
-    return;
+  configured.run([] {
+    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp))));
+    ECFFT_CUDA(cudaFuncSetAttribute(k_extend_sym_tma<NT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((1u << 11) * sizeof(Fp))));
+  });
+  const size_t smem = ((size_t)sizeof(Fp)) << p.log_t;
+  if (tma_enabled()) {
+    alignas(64) CUtensorMap map;
+    if (make_tile_map(p, &map)) {
+      launch_kernel(k_extend_sym_tma<NT, MINB>, tiles, NT, smem, st, p, map);
+      return;
+    }
   }
-  k_extend_sym<NT, MINB><<<(unsigned)tiles, NT, ((size_t)sizeof(Fp)) << p.log_t, st>>>(p);
+  launch_kernel(k_extend_sym<NT, MINB>, tiles, NT, smem, st, p);
 }
 
 // algorithmic bytes (level-streaming model of the reference algorithm): every level reads and writes each
@@ -456,7 +653,10 @@ static double pass_alg_bytes(const SymParams& p) {
   return levels * 64.0 * (double)p.total + mats + (p.comb ? 128.0 * (double)p.total : 0.0);
 }
 
-static void launch_sym(const SymParams& p, cudaStream_t st) {
+static void launch_sym(const SymParams& p_in, cudaStream_t st) {
+  SymParams p = p_in;
+  p.pf = tw_prefetch_mode();
+  p.tma_fence = tma_enabled() == 2;
   const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
   if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
   const bool timed = prof::enabled();
@@ -513,6 +713,8 @@ bool plan_extend_sym(SymFlow& flow, const Fp* tw_d, const Fp* tw_r, const Fp* ct
     p.xnn = comb->xnn;
     p.gam = comb->gam;
     p.gx = comb->gx;
+    p.ce0 = comb->e0;
+    p.ce1 = comb->e1;
   }
   const uint32_t need = log_h + (comb ? 1 : 0);  // tile bits that hold a whole vector (pair)
   if (need <= LT) {

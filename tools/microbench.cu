@@ -131,6 +131,61 @@ __global__ void __launch_bounds__(256) k_mul_mont(Fp* out, const Fp* in) {
   fp_store(out + t, x);
 }
 
+// ---- the second multiplier: a 256 x 256 -> 520-bit product on the FP64 pipe (52-bit limbs, 5 x 5 partial products,
+// each split exactly into high and low 52 bits by two round-toward-zero FMAs; the column sums are integer adds on
+// the raw bit patterns).  CORE ONLY: no conversion from / to 32-bit limbs and no reduction mod p, so the rate printed
+// is an UPPER bound on what a DFMA-based field product could reach.
+__device__ __forceinline__ void dfma_core(const double (&a)[5], const double (&b)[5], long long (&col)[10]) {
+  const double C1 = 20282409603651670423947251286016.0;                 // 2^104
+  const double C2 = 20282409603651670423947251286016.0 + 4503599627370496.0;  // 2^104 + 2^52
+#pragma unroll
+  for (int k = 0; k < 10; k++) col[k] = 0;
+#pragma unroll
+  for (int i = 0; i < 5; i++)
+#pragma unroll
+    for (int j = 0; j < 5; j++) {
+      const double hi = __fma_rz(a[i], b[j], C1);
+      const double lo = __fma_rz(a[i], b[j], C2 - hi);
+      col[i + j + 1] += __double_as_longlong(hi);
+      col[i + j] += __double_as_longlong(lo);
+    }
+}
+__device__ __forceinline__ double limb52(long long c) {   // low 52 bits of a column as an exact double
+  return __longlong_as_double((c & 0xFFFFFFFFFFFFFll) | 0x4330000000000000ll) - 4503599627370496.0;
+}
+__global__ void __launch_bounds__(256) k_mul_dfma(double* out, const double* in) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double a[5], b[5];
+  for (int i = 0; i < 5; i++) { a[i] = limb52((long long)(in[t + i] * 1e9)); b[i] = limb52((long long)(in[t + 5 + i] * 3e9) + i); }
+  long long col[10];
+  for (int it = 0; it < MITERS; it++) {
+    dfma_core(a, b, col);
+#pragma unroll
+    for (int i = 0; i < 5; i++) a[i] = limb52(col[i] ^ col[i + 5]);
+  }
+  double r = 0; for (int i = 0; i < 5; i++) r += a[i];
+  out[t] = r;
+}
+// one integer-pipe product and one FP64-pipe product core per iteration, independent chains: is the second one free?
+__global__ void __launch_bounds__(256) k_mul_both(Fp* out, const Fp* in, const double* din, int with_dfma) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  Fp x = fp_load(in + t), c = fp_load(in + t + 1);
+  double a[5], b[5];
+  for (int i = 0; i < 5; i++) { a[i] = limb52((long long)(din[t + i] * 1e9)); b[i] = limb52((long long)(din[t + 5 + i] * 3e9) + i); }
+  long long col[10];
+  for (int it = 0; it < MITERS; it++) {
+    x = fp_mul_lazy(x, c); c.v[0] ^= x.v[7];
+    if (with_dfma) {
+      dfma_core(a, b, col);
+#pragma unroll
+      for (int i = 0; i < 5; i++) a[i] = limb52(col[i] ^ col[i + 5]);
+    }
+  }
+  double r = 0; for (int i = 0; i < 5; i++) r += a[i];
+  x.v[0] ^= (uint32_t)__double_as_longlong(r);
+  fp_store(out + t, fp_canon(x));
+}
+
 template <typename F>
 float time_ms(F launch, int reps = 5) {
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -179,6 +234,12 @@ int main() {
     printf("bps=%d bfly_lazy   %8.2f Gbfly/s (%.2f Gmul/s)\n", bps, nthr * MITERS / ms * 1e-6, 4 * nthr * MITERS / ms * 1e-6);
     ms = time_ms([&] { k_bfly_norm<<<blocks, threads>>>((Fp*)buf, (const Fp*)inb); });
     printf("bps=%d bfly_norm   %8.2f Gbfly/s (%.2f Gmul/s)\n", bps, nthr * MITERS / ms * 1e-6, 2 * nthr * MITERS / ms * 1e-6);
+    ms = time_ms([&] { k_mul_dfma<<<blocks, threads>>>((double*)buf, (const double*)inb); });
+    printf("bps=%d mul_dfma_core %6.2f Gmul/s (52-bit limbs, 50 DFMA + 25 DADD + 50 int64 adds; no conversion, no reduction)\n", bps, nthr * MITERS / ms * 1e-6);
+    float ms0 = time_ms([&] { k_mul_both<<<blocks, threads>>>((Fp*)buf, (const Fp*)inb, (const double*)inb, 0); });
+    float ms1 = time_ms([&] { k_mul_both<<<blocks, threads>>>((Fp*)buf, (const Fp*)inb, (const double*)inb, 1); });
+    printf("bps=%d imad only %6.2f Gmul/s; imad + dfma core side by side %6.2f Gmul/s in total (%.2fx the time)\n", bps,
+           nthr * MITERS / ms0 * 1e-6, 2 * nthr * MITERS / ms1 * 1e-6, ms1 / ms0);
   }
   return 0;
 }
