@@ -41,11 +41,16 @@ def modmuls_per_elem(log_n):
 
 def products_per_elem(log_n):
     """256-bit field products THIS engine executes per coefficient of ENTER(n) (symmetric butterflies):
-    depth with vectors of length 2^L: pre-scale 1 (L >= 1), 2 L levels of 1/2 product per element, minus the
-    merged centre level (L >= 2), combine 3/2."""
+    depth with vectors of length 2^L: 2 L levels of 1/2 product per element, minus the merged centre level
+    (L >= 2), and a combine of 2 (both outputs two-product dots: the next depth's pre-scale rides in the tables).
+    With ECFFT_B200_FOLD=0: pre-scale 1 (L >= 1) and a combine of 3/2."""
+    fold = os.environ.get("ECFFT_B200_FOLD", "1") != "0"
     tot = 0.0
     for L in range(log_n):
-        tot += L + (1 if L >= 1 else 0) - (0.5 if L >= 2 else 0) + 1.5
+        if fold:
+            tot += L - (0.5 if L >= 2 else 0) + 2.0
+        else:
+            tot += L + (1 if L >= 1 else 0) - (0.5 if L >= 2 else 0) + 1.5
     return tot
 
 

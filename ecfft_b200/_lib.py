@@ -35,7 +35,7 @@ SYMBOLS = [
     "ecfft_mg_arena_alloc", "ecfft_mg_arena_open", "ecfft_mg_arena_close", "ecfft_mg_arena_free", "ecfft_mg_arena_reset", "ecfft_mg_arena_status",
     "ecfft_mg_signal_dev", "ecfft_mg_wait_dev", "ecfft_mg_arena_bytes", "ecfft_enter_peer_dev",
     "ecfft_selftest_field", "ecfft_flow_stats", "ecfft_pointwise_mul", "ecfft_pointwise_mul_dev",
-    "ecfft_mg_exit_arena_bytes", "ecfft_exit_peer_dev",
+    "ecfft_mg_exit_arena_bytes", "ecfft_exit_peer_dev", "ecfft_enter_many",
 ]
 
 
@@ -80,6 +80,7 @@ def load():
     for name in ("ecfft_extend", "ecfft_mextend"):
         getattr(L, name).argtypes = [vp, vp, sz, ci, vp]
     L.ecfft_degree.argtypes = [vp, vp, sz, psz]
+    L.ecfft_enter_many.argtypes = [vp, vp, sz, sz, vp]
     for name in ("ecfft_redc_z0", "ecfft_redc_z1"):
         getattr(L, name).argtypes = [vp, vp, vp, sz, vp]
     L.ecfft_modular_reduce.argtypes = [vp, vp, vp, vp, sz, vp]

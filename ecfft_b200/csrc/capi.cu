@@ -313,6 +313,64 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
     io.out(evals, d_out, n);
   });
 }
+// `count` coefficient vectors of n elements each, contiguous in host memory, to `count` evaluation vectors: the
+// loop a caller of FFTree::enter (src/fftree.rs:164) writes around it, as ONE call, so that the upload of vector
+// i+1 and the download of vector i-1 run on the copy engines while vector i is in the kernels (PCIe is full
+// duplex): per vector the host-to-host cost tends to the device time instead of device time + both copies.
+int ecfft_enter_many(const ecfft_tree* t, const uint64_t* coeffs, size_t n, size_t count, uint64_t* evals) {
+  return guard([&] {
+    LOCKED_IO
+    eng.level_for(n);
+    require((coeffs != nullptr && evals != nullptr) || n == 0 || count == 0, ERR_INVALID_ARG, "null buffer");
+    if (count == 0 || n == 0) return;
+    const int S = count > 1 ? 2 : 1;
+    Fp* d_in[2] = {io.alloc(n), S > 1 ? io.alloc(n) : nullptr};
+    Fp* d_out[2] = {io.alloc(n), S > 1 ? io.alloc(n) : nullptr};
+    cudaStream_t up = nullptr, down = nullptr;
+    cudaEvent_t u_done[2] = {nullptr, nullptr}, c_done[2] = {nullptr, nullptr}, d_done[2] = {nullptr, nullptr};
+    auto cleanup = [&] {
+      if (up) { cudaStreamSynchronize(up); cudaStreamDestroy(up); }
+      if (down) { cudaStreamSynchronize(down); cudaStreamDestroy(down); }
+      for (int i = 0; i < 2; i++) {
+        if (u_done[i]) cudaEventDestroy(u_done[i]);
+        if (c_done[i]) cudaEventDestroy(c_done[i]);
+        if (d_done[i]) cudaEventDestroy(d_done[i]);
+      }
+    };
+    try {
+      ECFFT_CUDA(cudaStreamCreateWithFlags(&up, cudaStreamNonBlocking));
+      ECFFT_CUDA(cudaStreamCreateWithFlags(&down, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; i++) {
+        ECFFT_CUDA(cudaEventCreateWithFlags(&u_done[i], cudaEventDisableTiming));
+        ECFFT_CUDA(cudaEventCreateWithFlags(&c_done[i], cudaEventDisableTiming));
+        ECFFT_CUDA(cudaEventCreateWithFlags(&d_done[i], cudaEventDisableTiming));
+      }
+      // the buffers were allocated on io.st: the copy streams start after that point
+      ECFFT_CUDA(cudaEventRecord(c_done[0], io.st));
+      ECFFT_CUDA(cudaStreamWaitEvent(up, c_done[0], 0));
+      ECFFT_CUDA(cudaStreamWaitEvent(down, c_done[0], 0));
+      for (size_t i = 0; i < count; i++) {
+        const int b = (int)(i % (size_t)S);
+        if (i >= (size_t)S) ECFFT_CUDA(cudaStreamWaitEvent(up, c_done[b], 0));        // vector i-S has left d_in[b]
+        ECFFT_CUDA(cudaMemcpyAsync(d_in[b], coeffs + 4 * i * n, n * sizeof(Fp), cudaMemcpyHostToDevice, up));
+        ECFFT_CUDA(cudaEventRecord(u_done[b], up));
+        ECFFT_CUDA(cudaStreamWaitEvent(io.st, u_done[b], 0));
+        if (i >= (size_t)S) ECFFT_CUDA(cudaStreamWaitEvent(io.st, d_done[b], 0));     // vector i-S has left d_out[b]
+        eng.enter(d_in[b], d_out[b], n);
+        ECFFT_CUDA(cudaEventRecord(c_done[b], io.st));
+        ECFFT_CUDA(cudaStreamWaitEvent(down, c_done[b], 0));
+        ECFFT_CUDA(cudaMemcpyAsync(evals + 4 * i * n, d_out[b], n * sizeof(Fp), cudaMemcpyDeviceToHost, down));
+        ECFFT_CUDA(cudaEventRecord(d_done[b], down));
+      }
+      ECFFT_CUDA(cudaStreamSynchronize(down));
+      ECFFT_CUDA(cudaStreamSynchronize(io.st));
+    } catch (...) {
+      cleanup();
+      throw;
+    }
+    cleanup();
+  });
+}
 int ecfft_exit(const ecfft_tree* t, const uint64_t* evals, size_t n, uint64_t* coeffs) {
   return guard([&] {
     LOCKED_IO

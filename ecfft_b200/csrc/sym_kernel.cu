@@ -227,16 +227,18 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
     if (threadIdx.x == 0) {
       const uint32_t rs = p.packed ? p.log_t : p.row_shift;           // the tensor map's row length is 2^rs elements
       const uint32_t lc = p.packed ? p.log_t : p.log_c, kr = p.packed ? 0u : p.krows;
-      const uint32_t bc_log = lc < 8 ? lc : 8;                        // box: 2^bc_log columns x 2^kr rows
-      const uint32_t nchunk = 1u << (lc - bc_log), npair = p.pair ? 2u : 1u;
+      const uint32_t bc_log = lc < 8 ? lc : 8;                        // box: 2^bc_log columns x 2^krb rows (dense in shared memory,
+      const uint32_t krb = lc > 8 ? 0u : kr;                          //  so a row wider than a box goes row by row)
+      const uint32_t nchunk = 1u << (lc - bc_log), nrow = 1u << (kr - krb), npair = p.pair ? 2u : 1u;
       const int c1 = (int)(gbase & ((1ull << rs) - 1)), c2 = (int)(gbase >> rs);
       if (p.tma_fence) asm volatile("fence.proxy.async;" ::: "memory");   // debugging aid (ECFFT_B200_TMA=2)
       mbar_expect_tx(mbar, T * (uint32_t)sizeof(Fp));
       for (uint32_t hf = 0; hf < 2; hf++)
         for (uint32_t pb = 0; pb < npair; pb++)
-          for (uint32_t cc = 0; cc < nchunk; cc++)
-            tma_load_3d(&s.s[hf * T + (pb << (kr + lc)) + (cc << bc_log)], tmap, (int)(hf * 4), c1 + (int)(cc << bc_log),
-                        c2 + (int)(pb << (p.log_h - rs)), mbar);
+          for (uint32_t rw = 0; rw < nrow; rw++)
+            for (uint32_t cc = 0; cc < nchunk; cc++)
+              tma_load_3d(&s.s[hf * T + (pb << (kr + lc)) + (rw << lc) + (cc << bc_log)], tmap, (int)(hf * 4), c1 + (int)(cc << bc_log),
+                          c2 + (int)(pb << (p.log_h - rs)) + (int)rw, mbar);
     }
     if (p.pf) prefetch_stage<NT>(p, tm, cur, T, p.pre != nullptr);
     mbar_wait(mbar, 0);
@@ -562,16 +564,20 @@ static bool pdl_enabled() {
   }
   return v != 0;
 }
-// ECFFT_B200_TMA (default 0): tile loads as cp.async.bulk.tensor copies completing on an mbarrier
+// ECFFT_B200_TMA (default 1): tile loads as cp.async.bulk.tensor copies completing on an mbarrier; 0 = cp.async.
+// Measured on one B200, same box, bit-identical results (profiles/r02_m_ab_tma.txt): ENTER 2^22 14.27 -> 13.95 ms,
+// 2^19 2.097 -> 2.070 ms, EXTEND 2^20 0.356 -> 0.350 ms, EXIT 2^22 31.19 -> 31.08 ms (its strided-view passes keep cp.async).
 static int tma_enabled() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ECFFT_B200_TMA");
-    v = e ? atoi(e) : 0;
+    v = e ? atoi(e) : 1;
   }
   return v;
 }
-// ECFFT_B200_TW_PREFETCH: 0 = off, 1 = next stage's twiddles into L1, 2 = into L2
+// ECFFT_B200_TW_PREFETCH: 0 = off (default), 1 = next stage's twiddles into L1, 2 = into L2.  Measured slower
+// (ENTER 2^22 14.87 -> 15.09 / 15.07 ms, profiles/r02_j_ab_tma_prefetch_enter22.txt): the loads it hides were
+// already covered by the other resident CTAs, and the address arithmetic costs issue slots.
 static uint32_t tw_prefetch_mode() {
   static int v = -1;
   if (v < 0) {
@@ -605,7 +611,7 @@ static bool make_tile_map(const SymParams& p, CUtensorMap* map) {
   const uint32_t bc_log = lc < 8 ? lc : 8;
   const cuuint64_t dims[3] = {8, (cuuint64_t)1 << rs, (cuuint64_t)(p.total >> rs)};
   const cuuint64_t strides[2] = {sizeof(Fp), (cuuint64_t)sizeof(Fp) << rs};   // bytes, dimensions 1 and 2
-  const cuuint32_t box[3] = {4, 1u << bc_log, 1u << kr};
+  const cuuint32_t box[3] = {4, 1u << bc_log, lc > 8 ? 1u : 1u << kr};
   const cuuint32_t estr[3] = {1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<Fp*>(p.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;

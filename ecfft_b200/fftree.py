@@ -190,6 +190,20 @@ class FFTree:
         """coefficients (low -> high) -> evaluations at the leaves"""
         return self._call("ecfft_enter", [coeffs], len(coeffs))
 
+    def enter_many(self, coeffs, out=None):
+        """`count` coefficient vectors, shape (count, n, 4) host array -> (count, n, 4) evaluations, as one pipelined
+        call (uploads and downloads overlap the kernels of the neighbouring vectors).  `out`: optional destination
+        (e.g. page-locked memory)."""
+        a = np.ascontiguousarray(coeffs, dtype=np.uint64)
+        if a.ndim != 3 or a.shape[2] != 4:
+            raise EcfftError(_lib.ERR_INVALID_ARG, "expected a (count, n, 4) array of u64 limbs")
+        if out is None:
+            out = np.empty_like(a)
+        elif out.shape != a.shape or out.dtype != np.uint64 or not out.flags.c_contiguous:
+            raise EcfftError(_lib.ERR_INVALID_ARG, "out must be a C-contiguous uint64 array of the input's shape")
+        _lib.check(self._L.ecfft_enter_many(self._h, _p(a), a.shape[1], a.shape[0], _p(out)))
+        return out
+
     def exit(self, evals):
         """evaluations -> coefficients"""
         return self._call("ecfft_exit", [evals], len(evals))

@@ -78,6 +78,10 @@ int ecfft_tree_table(const ecfft_tree* t, size_t subtree_leaves, const char* nam
 /* ---- the FFTree<F> algorithms, host buffers ------------------------------------------- */
 int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t* evals);            /* :164 */
 int ecfft_exit(const ecfft_tree* t, const uint64_t* evals, size_t n, uint64_t* coeffs);             /* :227 */
+/* `count` calls of ecfft_enter on consecutive vectors (coeffs, evals: count * n elements) as one pipelined call: the
+ * upload of vector i+1 and the download of vector i-1 overlap the kernels of vector i.  What a caller's loop around
+ * FFTree::enter (src/fftree.rs:164; benches/fftree.rs:28-33 calls it per polynomial) costs on a device. */
+int ecfft_enter_many(const ecfft_tree* t, const uint64_t* coeffs, size_t n, size_t count, uint64_t* evals);
 int ecfft_extend(const ecfft_tree* t, const uint64_t* evals, size_t n, int moiety, uint64_t* out);  /* :123 */
 int ecfft_mextend(const ecfft_tree* t, const uint64_t* evals, size_t n, int moiety, uint64_t* out); /* :138 */
 int ecfft_degree(const ecfft_tree* t, const uint64_t* evals, size_t n, size_t* degree);             /* :195 */

@@ -442,6 +442,39 @@ def test_host_buffer_enter_pipeline_equals_device_path(tree22, oracle_mod):
         eq(host, dev.cpu().numpy().view(np.uint64))
 
 
+def test_enter_many_equals_single_calls(trees, tree22, oracle_mod):
+    """ecfft_enter_many pipelines uploads, kernels and downloads of consecutive vectors over two buffer sets:
+    every vector must equal its own ecfft_enter (oracle-exact at 2^12; odd and even counts, count 1, count 0)"""
+    import ecfft_b200
+    gpu, cpu = trees
+    xs = np.stack([oracle_mod.random_elements(1 << 12, seed=70 + i) for i in range(5)])
+    ys = gpu.enter_many(xs)
+    for i in range(5):
+        eq(ys[i], cpu.enter(xs[i]))
+    eq(gpu.enter_many(xs[:1])[0], ys[0])
+    assert gpu.enter_many(xs[:0]).shape == (0, 1 << 12, 4)
+    big = np.stack([oracle_mod.random_elements(1 << 18, seed=80 + i) for i in range(4)])
+    out = tree22.enter_many(big)
+    for i in range(4):
+        eq(out[i], tree22.enter(big[i]))
+    with pytest.raises(ecfft_b200.EcfftError) as e:
+        gpu.enter_many(np.zeros((2, 3, 4), dtype=np.uint64))      # src/fftree.rs:490: not a power of two
+    assert e.value.code == ecfft_b200._lib.ERR_NOT_POW2
+
+
+def test_folded_combines_equal_the_plain_schedule(tree22, oracle_mod):
+    """ENTER stores the data between two depths pre-multiplied by the next EXTEND's pre-scale (Engine::enter_range_serial);
+    enter_range starts and ends in plain form wherever the range is cut, so every cut of the depth range must
+    give the same result as the whole ENTER — and that is oracle-exact on the 2^14 sub-lattice (other tests)."""
+    import torch
+    n = 1 << 16
+    x = torch.from_numpy(oracle_mod.random_elements(n, seed=90).view(np.int64)).cuda()
+    whole = tree22.enter(x)
+    for cut in (2, 1 << 5, 1 << 10, 1 << 11, 1 << 15):
+        part = tree22.enter_range(tree22.enter_range(x, 1, cut), cut, n)
+        assert torch.equal(part, whole), cut
+
+
 def test_device_field_selftest_drives_the_rare_carry_paths():
     """fp_add_lazy_f / fp_sub_lazy2_f branch on a carry out of the low two limbs (probability ~2^-31 on random
     data, i.e. about once per ENTER(2^22)): directed operands on the device itself, against canonical
