@@ -2,3 +2,4 @@
 from ._lib import EcfftError, LIB_PATH  # noqa: F401
 from .fftree import FFTree, Moiety, build_fftree, PARTS_FULL, PARTS_ENTER_ONLY  # noqa: F401
 from .poly import poly_mul  # noqa: F401
+from . import m31  # noqa: F401  (FFTree<m31::Fp>, the reference's second field)

@@ -36,6 +36,10 @@ SYMBOLS = [
     "ecfft_mg_signal_dev", "ecfft_mg_wait_dev", "ecfft_mg_arena_bytes", "ecfft_enter_peer_dev",
     "ecfft_selftest_field", "ecfft_flow_stats", "ecfft_pointwise_mul", "ecfft_pointwise_mul_dev",
     "ecfft_mg_exit_arena_bytes", "ecfft_exit_peer_dev", "ecfft_enter_many",
+    "ecfft_m31_tree_build", "ecfft_m31_tree_free", "ecfft_m31_tree_leaves", "ecfft_m31_tree_table",
+    "ecfft_m31_enter", "ecfft_m31_exit", "ecfft_m31_extend", "ecfft_m31_mextend", "ecfft_m31_degree",
+    "ecfft_m31_redc_z0", "ecfft_m31_redc_z1", "ecfft_m31_modular_reduce", "ecfft_m31_vanish",
+    "ecfft_m31_enter_dev", "ecfft_m31_exit_dev", "ecfft_m31_extend_dev",
 ]
 
 
@@ -115,6 +119,23 @@ def load():
     L.ecfft_mg_signal_dev.argtypes = [vp, ctypes.c_ulonglong, vp]
     L.ecfft_mg_wait_dev.argtypes = [vp, ctypes.c_ulonglong, ctypes.c_uint, vp]
     L.ecfft_flow_stats.argtypes = [ci, ctypes.POINTER(ctypes.c_ulonglong)]
+    L.ecfft_m31_tree_build.argtypes = [sz, ci, pvp]
+    L.ecfft_m31_tree_free.argtypes = [vp]
+    L.ecfft_m31_tree_free.restype = None
+    L.ecfft_m31_tree_leaves.argtypes = [vp]
+    L.ecfft_m31_tree_leaves.restype = sz
+    L.ecfft_m31_tree_table.argtypes = [vp, sz, ctypes.c_char_p, vp, sz, psz]
+    for name in ("ecfft_m31_enter", "ecfft_m31_exit", "ecfft_m31_vanish"):
+        getattr(L, name).argtypes = [vp, vp, sz, vp]
+    for name in ("ecfft_m31_extend", "ecfft_m31_mextend"):
+        getattr(L, name).argtypes = [vp, vp, sz, ci, vp]
+    L.ecfft_m31_degree.argtypes = [vp, vp, sz, psz]
+    for name in ("ecfft_m31_redc_z0", "ecfft_m31_redc_z1"):
+        getattr(L, name).argtypes = [vp, vp, vp, sz, vp]
+    L.ecfft_m31_modular_reduce.argtypes = [vp, vp, vp, vp, sz, vp]
+    for name in ("ecfft_m31_enter_dev", "ecfft_m31_exit_dev"):
+        getattr(L, name).argtypes = [vp, vp, sz, vp, vp]
+    L.ecfft_m31_extend_dev.argtypes = [vp, vp, sz, ci, vp, vp]
     L.ecfft_launch_count.restype = ctypes.c_ulonglong
     L.ecfft_launch_count.argtypes = []
     L.ecfft_profile_enable.restype = None

@@ -16,6 +16,7 @@ struct ecfft_tree {
 };
 
 static thread_local std::string g_last_error;
+namespace ecfft { void set_last_error(const char* msg) { g_last_error = msg ? msg : ""; } }   // for the other ABI files (m31.cu)
 
 template <class F>
 static int guard(F f) {

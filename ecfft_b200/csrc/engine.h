@@ -358,6 +358,8 @@ size_t peer_exit_arena_bytes(size_t n, int world);
 void exit_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int world, void* const* bases,
                unsigned long long epoch, Fp* out_chunk);
 
+void set_last_error(const char* msg);   // capi.cu: the message ecfft_last_error() returns on this thread
+
 // ---- builder.cu / serialize.cu --------------------------------------------------------------
 Tree* build_secp256k1(size_t n, int parts, int device);                                     // lib.rs:39-85
 Tree* tree_from_leaves(const Fp* leaves_dev_plain, size_t n, const std::vector<RatMapHost>& maps, int parts, int device);  // fftree.rs:42-70

@@ -142,6 +142,7 @@ struct ecfft_m31_tree {
   ecfft::m31::F* f = nullptr;                 // 2n, BinaryTree order (f[0] = 0); chain level N reads it with stride n/N
   std::vector<ecfft::m31::Lv> lv;             // lv[k]: 2^k leaves
   std::vector<ecfft::m31::Map> maps;
+  ecfft::m31::F leaf2[2] = {0, 0};            // leaves of the 2-leaf chain level (VANISH base case, src/fftree.rs:293-298)
   cudaStream_t st = nullptr;
   std::vector<void*> owned;
   std::mutex mu;
@@ -283,7 +284,13 @@ struct Eng {
     const uint32_t log_h = ilog2(h);
     F* t0 = tmp(h * nvec);
     F* g1 = tmp(h * nvec);
-    map(h * nvec, st, [=] __device__(size_t k) { t0[k] = fmul(evals[2 * k], finv(__ldg(a + 2 * (k & (h - 1))))); });
+    // the reference batch-inverts a[::2] on every call (src/fftree.rs:235); for a = xnn_s the stored inverses are the same values
+    if (a == lv.xnn) {
+      const F* ai = lv.xnn_inv;
+      map(h * nvec, st, [=] __device__(size_t k) { t0[k] = fmul(evals[2 * k], __ldg(ai + 2 * (k & (h - 1)))); });
+    } else {
+      map(h * nvec, st, [=] __device__(size_t k) { t0[k] = fmul(evals[2 * k], finv(__ldg(a + 2 * (k & (h - 1))))); });
+    }
     extend(t0, g1, log_h, nvec, 1 - moiety);
     F* h1 = t0;
     map(h * nvec, st, [=] __device__(size_t k) {
@@ -382,7 +389,7 @@ struct Eng {
     F* Q2 = tmp(2 * n);
     F* q0 = tmp(n);
     F* e = tmp(n);
-    const F l0 = leaf2[0], l1 = leaf2[1];
+    const F l0 = t.leaf2[0], l1 = t.leaf2[1];
     map(n, st, [=] __device__(size_t i) {
       Q[2 * i] = fsub(dom[i], l0);
       Q[2 * i + 1] = fsub(dom[i], l1);
@@ -408,7 +415,6 @@ struct Eng {
     }
     ECFFT_CUDA(cudaMemcpyAsync(out, Q, 2 * n * sizeof(F), cudaMemcpyDeviceToDevice, st));
   }
-  F leaf2[2] = {0, 0};   // leaves of the 2-leaf chain level (VANISH base case, src/fftree.rs:293-298)
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -699,8 +705,8 @@ static void build_level(Tree& t, uint32_t k, Eng& eng) {
       zz0[0] = zz0[1] = fmul(s0, s0);
       zz1[0] = zz1[1] = fmul(s1, s1);
     });
-    ECFFT_CUDA(cudaMemcpyAsync(&eng.leaf2[0], leaves, sizeof(F), cudaMemcpyDeviceToHost, st));
-    ECFFT_CUDA(cudaMemcpyAsync(&eng.leaf2[1], leaves + stride, sizeof(F), cudaMemcpyDeviceToHost, st));
+    ECFFT_CUDA(cudaMemcpyAsync(&t.leaf2[0], leaves, sizeof(F), cudaMemcpyDeviceToHost, st));
+    ECFFT_CUDA(cudaMemcpyAsync(&t.leaf2[1], leaves + stride, sizeof(F), cudaMemcpyDeviceToHost, st));
     ECFFT_CUDA(cudaStreamSynchronize(st));
   } else {
     const Lv& sub = t.lv[k - 1];
@@ -787,17 +793,16 @@ static void build_level(Tree& t, uint32_t k, Eng& eng) {
 // ---------------------------------------------------------------------------------------------------------
 using namespace ecfft;
 namespace {
-thread_local std::string g_m31_error;
 template <class Fn>
 int guard31(Fn fn) {
   try {
     fn();
     return ECFFT_OK;
   } catch (const Error& e) {
-    ecfft_set_last_error(e.what());
+    set_last_error(e.what());
     return e.code;
   } catch (const std::exception& e) {
-    ecfft_set_last_error(e.what());
+    set_last_error(e.what());
     return ECFFT_ERR_INVALID_ARG;
   }
 }
@@ -809,12 +814,7 @@ struct Io {
   DeviceGuard dev;
   m31::Tree& t;
   m31::Eng eng;
-  Io(const ecfft_m31_tree* tree) : dev(tree->device), t(*const_cast<ecfft_m31_tree*>(tree)), eng(t, t.st) { eng.leaf2[0] = t.lv.size() > 1 ? leaf(0) : 0; eng.leaf2[1] = t.lv.size() > 1 ? leaf(1) : 0; }
-  m31::F leaf(int i) {
-    m31::F v = 0;
-    ECFFT_CUDA(cudaMemcpy(&v, t.f + t.n() + (size_t)i * (t.n() / 2), sizeof v, cudaMemcpyDeviceToHost));
-    return v;
-  }
+  Io(const ecfft_m31_tree* tree) : dev(tree->device), t(*const_cast<ecfft_m31_tree*>(tree)), eng(t, t.st) {}
   m31::F* in(const uint32_t* host, size_t n) {
     need(host != nullptr || n == 0, ERR_INVALID_ARG, "null input buffer");
     m31::F* d = eng.tmp(n);

@@ -187,6 +187,33 @@ int ecfft_exit_peer_dev(const ecfft_tree* t, const void* d_chunk, size_t n, int 
  * counters3 = { mismatches, additions that took the rare path, subtractions that did }. */
 int ecfft_selftest_field(int device, unsigned long long samples, unsigned long long* counters3);
 
+/* ---- the reference's second field: FFTree<m31::Fp> (src/lib.rs:190-215) ----------------------------------
+ * Elements are uint32_t holding the canonical value in [0, 2^31 - 1), which is what the reference's
+ * `ark_ff_optimized::fp31::Fp(pub u32)` keeps in memory (src/lib.rs:199-206 writes its constants that way).
+ * The handle owns the device tables of every chain level, built on the device by the same sequence as
+ * build_ec_fftree / FFTree::new / from_tree (src/ec.rs:498-554, src/fftree.rs:42-70, 318-463).  Same method
+ * surface, argument meaning and status codes as the secp256k1 entry points above; ECFFT_ERR_TOO_LARGE when
+ * log2 n > 28 (build_ec_fftree returns None, src/ec.rs:513-515). */
+typedef struct ecfft_m31_tree ecfft_m31_tree;
+int ecfft_m31_tree_build(size_t n, int device, ecfft_m31_tree** out);                                            /* lib.rs:197 */
+void ecfft_m31_tree_free(ecfft_m31_tree* t);
+size_t ecfft_m31_tree_leaves(const ecfft_m31_tree* t);
+/* same table names as ecfft_tree_table; matrices are 4 values each (row major) */
+int ecfft_m31_tree_table(const ecfft_m31_tree* t, size_t subtree_leaves, const char* name, uint32_t* out, size_t cap_elems, size_t* count);
+int ecfft_m31_enter(const ecfft_m31_tree* t, const uint32_t* coeffs, size_t n, uint32_t* evals);                 /* fftree.rs:164 */
+int ecfft_m31_exit(const ecfft_m31_tree* t, const uint32_t* evals, size_t n, uint32_t* coeffs);                  /* :227 */
+int ecfft_m31_extend(const ecfft_m31_tree* t, const uint32_t* evals, size_t n, int moiety, uint32_t* out);       /* :123 */
+int ecfft_m31_mextend(const ecfft_m31_tree* t, const uint32_t* evals, size_t n, int moiety, uint32_t* out);      /* :138 */
+int ecfft_m31_degree(const ecfft_m31_tree* t, const uint32_t* evals, size_t n, size_t* degree);                  /* :195 */
+int ecfft_m31_redc_z0(const ecfft_m31_tree* t, const uint32_t* evals, const uint32_t* a, size_t n, uint32_t* out); /* :264 */
+int ecfft_m31_redc_z1(const ecfft_m31_tree* t, const uint32_t* evals, const uint32_t* a, size_t n, uint32_t* out); /* :272 */
+int ecfft_m31_modular_reduce(const ecfft_m31_tree* t, const uint32_t* evals, const uint32_t* a, const uint32_t* c, size_t n, uint32_t* out); /* :286 */
+int ecfft_m31_vanish(const ecfft_m31_tree* t, const uint32_t* domain, size_t n, uint32_t* out);                  /* :313; out has 2n elements */
+/* operands resident in HBM, work enqueued on `stream` */
+int ecfft_m31_enter_dev(const ecfft_m31_tree* t, const void* d_coeffs, size_t n, void* d_evals, void* stream);
+int ecfft_m31_exit_dev(const ecfft_m31_tree* t, const void* d_evals, size_t n, void* d_coeffs, void* stream);
+int ecfft_m31_extend_dev(const ecfft_m31_tree* t, const void* d_evals, size_t n, int moiety, void* d_out, void* stream);
+
 /* ---- instrumentation used by bench.py ------------------------------------------------- */
 /* kernels launched by this library since it was loaded */
 unsigned long long ecfft_launch_count(void);
