@@ -380,6 +380,22 @@ def main():
         e2e_s = (time.perf_counter() - t0) / args.steps
         h2d = d2h = n * 32
         last_e2e_in = (args.steps - 1) % NBUF
+        # the same through ecfft_enter_many: a caller's loop over NBUF polynomials as one call, so that the copies of
+        # neighbouring vectors overlap the kernels (reported beside the single-call figure, never instead of it)
+        many_in = torch.empty((NBUF, n, 4), dtype=torch.int64).pin_memory()
+        for i in range(NBUF):
+            many_in[i].copy_(host_in[i])
+        many_out = torch.empty((NBUF, n, 4), dtype=torch.int64).pin_memory()
+        mi, mo = ctypes.c_void_p(many_in.data_ptr()), ctypes.c_void_p(many_out.data_ptr())
+        _lib.check(L.ecfft_enter_many(tree._h, mi, n, NBUF, mo))
+        reps_many = max(1, args.steps // NBUF)
+        t0 = time.perf_counter()
+        for _ in range(reps_many):
+            _lib.check(L.ecfft_enter_many(tree._h, mi, n, NBUF, mo))
+        extra["e2e_many_ms_per_vector"] = (time.perf_counter() - t0) / (reps_many * NBUF) * 1e3
+        extra["e2e_many_vectors_per_call"] = NBUF
+        extra["e2e_many_matches_single_call"] = bool((many_out[last_e2e_in] == host_out).all())
+        del many_in, many_out
     else:
         # every rank uploads its n/N coefficients from pinned memory, the ranks run the sharded ENTER and gather,
         # and RANK 0 downloads the WHOLE evaluation vector into its pinned memory — one consumer process ends up
@@ -429,7 +445,7 @@ def main():
                 f"{world} ranks: local ENTER(n/{world}) + 1 NCCL all-gather + top {world.bit_length() - 1} depths replicated" if args.multi_gpu == "allgather"
                 else f"{world} ranks: local ENTER(n/{world}), top {world.bit_length() - 1} depths sharded (pairwise NCCL send/recv per straddling level), final all-gather of the result" if args.multi_gpu == "sharded"
                 else f"{world} ranks: local ENTER(n/{world}), top {world.bit_length() - 1} depths sharded, straddling butterfly levels and combines read the partner's buffers over NVLink (CUDA-IPC peer memory, flag-ordered), final NCCL all-gather of the result"),
-            "inputs": f"{NBUF} rotating coefficient vectors of {n * 32 >> 20} MiB; tables 320 B/leaf resident in HBM; no explicit L2 flush (per-step stream >> 126 MB L2)",
+            "inputs": f"{NBUF} rotating coefficient vectors of {n * 32 >> 20} MiB; tables ~450 B/leaf resident in HBM; no explicit L2 flush (per-step stream >> 126 MB L2)",
             "tree_build_s": round(t_build, 3),
             "host": numa,
         },
@@ -470,6 +486,8 @@ def main():
         cfg = run_configs(args, tree, world, rank, local_rank, dev, timed, all_ranks_true)
         line.update(cfg)
         ok_all = ok_all and all(v for k, v in cfg.items() if k.endswith("_matches_single") or k.endswith("_roundtrip_ok") or k.endswith("_status_ok"))
+    if "e2e_many_matches_single_call" in line:
+        ok_all = ok_all and line["e2e_many_matches_single_call"]
     if "multi_gpu_matches_single" in line:
         ok_all = ok_all and line["multi_gpu_matches_single"]
 
@@ -547,6 +565,18 @@ def run_configs(args, tree22, world, rank, local_rank, dev, timed, all_ranks_tru
         out[f"cfg_exit_2p{args.log_n}_ms"] = ms
         out[f"cfg_exit_2p{args.log_n}_elems_per_s"] = (1 << args.log_n) / (ms * 1e-3)
         out[f"cfg_exit_2p{args.log_n}_roundtrip_ok"] = bool((tree.exit(ev) == xn).all())
+        del tree, xn, ev
+        torch.cuda.empty_cache()
+        # the reference's second field (src/lib.rs:190-215): FFTree<m31::Fp>, ENTER and EXIT at n = 2^20
+        t0 = time.perf_counter()
+        t31 = ecfft_b200.m31.build_fftree(1 << 20, device=local_rank)
+        torch.cuda.synchronize()
+        out["cfg_m31_tree_build_2p20_s"] = round(time.perf_counter() - t0, 3)
+        x31 = torch.randint(0, (1 << 31) - 1, (1 << 20,), dtype=torch.int32, device=dev)
+        out["cfg_m31_enter_2p20_ms"] = median_ms(lambda: t31.enter(x31))
+        e31 = t31.enter(x31)
+        out["cfg_m31_exit_2p20_ms"] = median_ms(lambda: t31.exit(e31), warm=1, reps=3)
+        out["cfg_m31_2p20_roundtrip_ok"] = bool((t31.exit(e31) == x31).all())
         return out
 
     # N > 1 — configs[3]: ENTER n = 2^24 sharded over the N GPUs (peer schedule + final all-gather)
