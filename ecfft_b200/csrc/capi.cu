@@ -2,6 +2,10 @@
 // host buffers through the handle's stream.  No torch types, no CPU fallback: every entry point
 // that computes needs a CUDA device and fails with ECFFT_ERR_CUDA without one.
 #include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <chrono>
 
 #include <mutex>
 
@@ -279,7 +283,9 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
     // the final download.  Splitting the deeper depths too costs more in extra launches on an under-filled GPU
     // than it hides (measured at n = 2^22: whole-vector ENTER 15.5 ms, two full half-ENTERs + merge 16.2 ms,
     // n/8,n/8,n/4,n/2 17.6 ms; tools/pcie_probe.py).
-    if (n >= ((size_t)1 << 16)) {
+    static const bool host_pipe = !(getenv("ECFFT_B200_HOST_PIPE") && atoi(getenv("ECFFT_B200_HOST_PIPE")) == 0);
+    static const bool host_trace = getenv("ECFFT_B200_HOST_TRACE") != nullptr;   // prints the call's device timeline (debugging aid)
+    if (n >= ((size_t)1 << 16) && host_pipe) {
       const size_t m_split = 1024;
       const size_t off[4] = {0, 3 * (n / 16), 8 * (n / 16), n};
       Fp* d_in = io.alloc(n);
@@ -287,25 +293,45 @@ int ecfft_enter(const ecfft_tree* t, const uint64_t* coeffs, size_t n, uint64_t*
       cudaStream_t cs = nullptr;
       ECFFT_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
       cudaEvent_t ev[3] = {nullptr, nullptr, nullptr};
+      cudaEvent_t tr[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+      const std::chrono::steady_clock::time_point t_host0 = std::chrono::steady_clock::now();
       try {
+        if (host_trace) {
+          for (int i = 0; i < 8; i++) ECFFT_CUDA(cudaEventCreate(&tr[i]));
+          ECFFT_CUDA(cudaEventRecord(tr[0], io.st));
+          ECFFT_CUDA(cudaStreamWaitEvent(cs, tr[0], 0));
+        }
         for (int g = 0; g < 3; g++) {
           ECFFT_CUDA(cudaEventCreateWithFlags(&ev[g], cudaEventDisableTiming));
           ECFFT_CUDA(cudaMemcpyAsync(d_in + off[g], coeffs + 4 * off[g], (off[g + 1] - off[g]) * sizeof(Fp), cudaMemcpyHostToDevice, cs));
           ECFFT_CUDA(cudaEventRecord(ev[g], cs));
+          if (host_trace) ECFFT_CUDA(cudaEventRecord(tr[1 + g], cs));
         }
         for (int g = 0; g < 3; g++) {
           ECFFT_CUDA(cudaStreamWaitEvent(io.st, ev[g], 0));
           eng.enter_range(d_in + off[g], d_mid + off[g], off[g + 1] - off[g], 1, m_split);
+          if (host_trace) ECFFT_CUDA(cudaEventRecord(tr[4 + g], io.st));
         }
         eng.enter_range(d_mid, d_out, n, m_split, n);
+        if (host_trace) ECFFT_CUDA(cudaEventRecord(tr[7], io.st));
+        const double ms_enqueue = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
         io.out(evals, d_out, n);
+        if (host_trace) {
+          float t[8] = {0};
+          for (int i = 1; i < 8; i++) cudaEventElapsedTime(&t[i], tr[0], tr[i]);
+          const double ms_total = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_host0).count();
+          fprintf(stderr, "[ecfft_enter trace] uploads done %.2f %.2f %.2f | chunk depths done %.2f %.2f %.2f | deep depths done %.2f | host: enqueued %.2f, returned %.2f ms\n",
+                  t[1], t[2], t[3], t[4], t[5], t[6], t[7], ms_enqueue, ms_total);
+        }
       } catch (...) {
         cudaStreamSynchronize(cs);
         cudaStreamDestroy(cs);
         for (int g = 0; g < 3; g++) if (ev[g]) cudaEventDestroy(ev[g]);
+        for (int i = 0; i < 8; i++) if (tr[i]) cudaEventDestroy(tr[i]);
         throw;
       }
       for (int g = 0; g < 3; g++) cudaEventDestroy(ev[g]);
+      for (int i = 0; i < 8; i++) if (tr[i]) cudaEventDestroy(tr[i]);
       cudaStreamDestroy(cs);
       return;
     }

@@ -211,6 +211,7 @@ struct SymParams {
   // out[(vector << (log_h + 1)) + i] and v0 = (E[(g << e_shift) + e_off] - u0) * Z[i] at the same place + h
   uint32_t split;
   uint32_t tma_fence;
+  uint32_t l2pf;              // strided tiles: bulk L2 prefetch of the tile's twiddle / combine-table ranges (set by launch_sym)
   uint32_t pf;                // twiddle prefetch ahead of each stage: 0 off, 1 into L1, 2 into L2 (set by launch_sym)
   // ---- flow fields (k_sym_flow: all passes of an ENTER in one persistent launch) ----
   uint32_t kind;              // 0: butterfly tile pass; 1: combine-only pass (in = [u1 | v1] unscaled, A = [u0 | v0])

@@ -93,6 +93,9 @@ __device__ __forceinline__ void tma_load_3d(void* smem, const CUtensorMap* map, 
                ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(map), "r"(c0), "r"(c1), "r"(c2),
                  "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
 }
+__device__ __forceinline__ void bulk_prefetch_l2(const void* p, unsigned bytes) {   // one instruction per contiguous range, no registers held
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
@@ -195,6 +198,46 @@ __device__ __forceinline__ void prefetch_stage(const SymParams& p, const TileMap
   }
 }
 
+// Bulk L2 prefetch of what a STRIDED tile will read through the read-only path later (ECFFT_B200_L2PF, one thread,
+// one cp.async.bulk.prefetch.L2 per contiguous range): the twiddles of its levels — level j needs, for every
+// combination of the row bits below j, 2^log_c consecutive entries — and, for the pair tile of ENTER's last pass,
+// the rows of u0 / v0 and of the combine tables.  In those passes a butterfly's twiddle has no reuse inside the tile
+// and the top recursion depths have few vectors to share lines with, so without this the loads go to DRAM when the
+// stage needs them (ncu source view: 23 % of the warps' time in such a launch waited on them).  Measured slower
+// all the same (see launch_sym): kept as a knob with its numbers, off by default.
+__device__ __forceinline__ void prefetch_tile_operands(const SymParams& p, uint32_t pos0, unsigned long long gbase) {
+  const uint32_t run = (uint32_t)sizeof(Fp) << p.log_c;
+  const uint32_t cpos = pos0 & ((1u << p.row_shift) - 1);          // column offset of the tile inside a row
+  for (uint32_t j = p.lvl_lo; j < p.lvl_hi; j++) {
+    const uint32_t nr = 1u << (j - p.row_shift);
+    for (uint32_t r = 0; r < nr; r++) {
+      const uint32_t idx = (1u << j) + (r << p.row_shift) + cpos;
+      if (p.do_d) bulk_prefetch_l2(p.tw_d + idx, run);
+      if (p.do_r) bulk_prefetch_l2(p.tw_r + idx, run);
+    }
+  }
+  if (p.comb) {
+    const uint32_t hmask = (1u << p.log_h) - 1;
+    for (uint32_t r = 0; r < (1u << p.krows); r++) {
+      const unsigned long long g = gbase + ((unsigned long long)r << p.row_shift);
+      const uint32_t i = (pos0 + (r << p.row_shift)) & hmask;
+      bulk_prefetch_l2(p.A + g, run);
+      bulk_prefetch_l2(p.A + g + ((unsigned long long)1 << p.log_h), run);
+      bulk_prefetch_l2(p.gam + i, run);
+      bulk_prefetch_l2(p.gx + i, run);
+      if (p.ce0) {
+        bulk_prefetch_l2(p.ce0 + i, run);
+        bulk_prefetch_l2(p.ce1 + i, run);
+      } else {
+        bulk_prefetch_l2(p.xnn + 2 * i, 2 * run);
+      }
+    }
+  } else if (p.post && !p.E) {
+    const uint32_t hmask = (1u << p.log_h) - 1;
+    for (uint32_t r = 0; r < (1u << p.krows); r++) bulk_prefetch_l2(p.post + ((pos0 + (r << p.row_shift)) & hmask), run);
+  }
+}
+
 // One tile of one pass.  Packed tiles start at element gbase_packed; strided tiles are tile `tile` of vector
 // (pair) w.  FLOW: the data buffers may have been written by other CTAs of the SAME launch, so every read of
 // them goes to L2 (cp.async.cg, ld.global.cg), never through L1.  TMA: the tile load is a bulk tensor copy.
@@ -220,6 +263,7 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
   }
   const StagePlan plan(p);
   Stage cur = plan.stage(p, 0);
+  if (!FLOW && p.l2pf && !p.packed && threadIdx.x == 32) prefetch_tile_operands(p, tm.pos0, gbase);
 
   // ---- tile load
   if (TMA) {
@@ -663,6 +707,9 @@ static void launch_sym(const SymParams& p_in, cudaStream_t st) {
   SymParams p = p_in;
   p.pf = tw_prefetch_mode();
   p.tma_fence = tma_enabled() == 2;
+  // default off: measured 2 % SLOWER at every size (ENTER 2^22 13.96 -> 14.26 ms, EXIT 31.1 -> 31.9 ms; profiles/r02_r_ab_l2pf.txt)
+  static const int l2pf = [] { const char* e = getenv("ECFFT_B200_L2PF"); return e ? atoi(e) : 0; }();
+  p.l2pf = l2pf != 0;
   const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
   if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
   const bool timed = prof::enabled();
