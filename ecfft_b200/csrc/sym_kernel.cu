@@ -206,14 +206,20 @@ __device__ __forceinline__ void prefetch_stage(const SymParams& p, const TileMap
 // stage needs them (ncu source view: 23 % of the warps' time in such a launch waited on them).  Measured slower
 // all the same (see launch_sym): kept as a knob with its numbers, off by default.
 __device__ __forceinline__ void prefetch_tile_operands(const SymParams& p, uint32_t pos0, unsigned long long gbase) {
+  // the 32 lanes of one warp share the ranges (range number mod 32 == lane)
+  const uint32_t lane = threadIdx.x & 31;
+  uint32_t cnt = 0;
+  auto pf = [&](const void* ptr, uint32_t bytes) {
+    if ((cnt++ & 31) == lane) bulk_prefetch_l2(ptr, bytes);
+  };
   const uint32_t run = (uint32_t)sizeof(Fp) << p.log_c;
   const uint32_t cpos = pos0 & ((1u << p.row_shift) - 1);          // column offset of the tile inside a row
   for (uint32_t j = p.lvl_lo; j < p.lvl_hi; j++) {
     const uint32_t nr = 1u << (j - p.row_shift);
     for (uint32_t r = 0; r < nr; r++) {
       const uint32_t idx = (1u << j) + (r << p.row_shift) + cpos;
-      if (p.do_d) bulk_prefetch_l2(p.tw_d + idx, run);
-      if (p.do_r) bulk_prefetch_l2(p.tw_r + idx, run);
+      if (p.do_d) pf(p.tw_d + idx, run);
+      if (p.do_r) pf(p.tw_r + idx, run);
     }
   }
   if (p.comb) {
@@ -221,20 +227,20 @@ __device__ __forceinline__ void prefetch_tile_operands(const SymParams& p, uint3
     for (uint32_t r = 0; r < (1u << p.krows); r++) {
       const unsigned long long g = gbase + ((unsigned long long)r << p.row_shift);
       const uint32_t i = (pos0 + (r << p.row_shift)) & hmask;
-      bulk_prefetch_l2(p.A + g, run);
-      bulk_prefetch_l2(p.A + g + ((unsigned long long)1 << p.log_h), run);
-      bulk_prefetch_l2(p.gam + i, run);
-      bulk_prefetch_l2(p.gx + i, run);
+      pf(p.A + g, run);
+      pf(p.A + g + ((unsigned long long)1 << p.log_h), run);
+      pf(p.gam + i, run);
+      pf(p.gx + i, run);
       if (p.ce0) {
-        bulk_prefetch_l2(p.ce0 + i, run);
-        bulk_prefetch_l2(p.ce1 + i, run);
+        pf(p.ce0 + i, run);
+        pf(p.ce1 + i, run);
       } else {
-        bulk_prefetch_l2(p.xnn + 2 * i, 2 * run);
+        pf(p.xnn + 2 * i, 2 * run);
       }
     }
   } else if (p.post && !p.E) {
     const uint32_t hmask = (1u << p.log_h) - 1;
-    for (uint32_t r = 0; r < (1u << p.krows); r++) bulk_prefetch_l2(p.post + ((pos0 + (r << p.row_shift)) & hmask), run);
+    for (uint32_t r = 0; r < (1u << p.krows); r++) pf(p.post + ((pos0 + (r << p.row_shift)) & hmask), run);
   }
 }
 
@@ -263,7 +269,8 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
   }
   const StagePlan plan(p);
   Stage cur = plan.stage(p, 0);
-  if (!FLOW && p.l2pf && !p.packed && threadIdx.x == 32) prefetch_tile_operands(p, tm.pos0, gbase);
+  // l2pf = 1: issued while the tile load is in flight; 2: after the tile has landed (the copy engine serves both)
+  if (!FLOW && p.l2pf == 1 && !p.packed && (threadIdx.x >> 5) == 1) prefetch_tile_operands(p, tm.pos0, gbase);
 
   // ---- tile load
   if (TMA) {
@@ -306,6 +313,8 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();
   }
+
+  if (!FLOW && p.l2pf == 2 && !p.packed && (threadIdx.x >> 5) == 1) prefetch_tile_operands(p, tm.pos0, gbase);
 
   // ---- stages
   for (uint32_t sidx = 0; sidx < plan.nstages; sidx++) {
@@ -709,7 +718,7 @@ static void launch_sym(const SymParams& p_in, cudaStream_t st) {
   p.tma_fence = tma_enabled() == 2;
   // default off: measured 2 % SLOWER at every size (ENTER 2^22 13.96 -> 14.26 ms, EXIT 31.1 -> 31.9 ms; profiles/r02_r_ab_l2pf.txt)
   static const int l2pf = [] { const char* e = getenv("ECFFT_B200_L2PF"); return e ? atoi(e) : 0; }();
-  p.l2pf = l2pf != 0;
+  p.l2pf = (uint32_t)l2pf;
   const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
   if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
   const bool timed = prof::enabled();
