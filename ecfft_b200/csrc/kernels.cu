@@ -22,6 +22,7 @@ static std::atomic<unsigned long long> g_launches{0};
 static std::atomic<bool> g_enabled{false};
 static std::mutex g_mu;
 static std::vector<Rec> g_recs;
+static thread_local cudaEvent_t t_open_end = nullptr;   // end event of the launch this host thread has bracketed and not yet closed
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 unsigned long long launches() { return g_launches.load(); }
 void enable(bool on) { g_enabled.store(on); }
@@ -33,12 +34,14 @@ void record_begin(Kernel k, double alg_bytes, cudaStream_t st) {
   ECFFT_CUDA(cudaEventCreate(&r.e0));
   ECFFT_CUDA(cudaEventCreate(&r.e1));
   ECFFT_CUDA(cudaEventRecord(r.e0, st));
+  t_open_end = r.e1;
   std::lock_guard<std::mutex> lock(g_mu);
   g_recs.push_back(r);
 }
-void record_end(cudaStream_t st) {
-  std::lock_guard<std::mutex> lock(g_mu);
-  ECFFT_CUDA(cudaEventRecord(g_recs.back().e1, st));
+void record_end(cudaStream_t st) {   // pairs with this thread's own record_begin, whatever other threads recorded meanwhile
+  if (!t_open_end) return;
+  ECFFT_CUDA(cudaEventRecord(t_open_end, st));
+  t_open_end = nullptr;
 }
 void read(Kernel k, double* ms, double* alg_bytes, unsigned long long* n) {
   std::lock_guard<std::mutex> lock(g_mu);

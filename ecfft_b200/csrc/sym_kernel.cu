@@ -652,10 +652,10 @@ static EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 // Tensor map of a pass's input: [total >> rs][2^rs][8 x u32], box {4, 2^min(log_c, 8), 2^krows}; false when the pass
-// does not have that shape (strided REDC views, batches that are not whole rows): the caller keeps cp.async.
+// does not have that shape (batches that are not whole rows, tiny tiles): the caller keeps cp.async.
 static bool make_tile_map(const SymParams& p, CUtensorMap* map) {
   EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc || p.in_shift || p.in_off || p.kind != 0) return false;
+  if (!enc || p.kind != 0 || p.in_shift > 4) return false;
   const uint32_t rs = p.packed ? p.log_t : p.row_shift;
   const uint32_t lc = p.packed ? p.log_t : p.log_c, kr = p.packed ? 0u : p.krows;
   if (p.log_t < 9) return false;   // shared-memory box addresses must be 128-byte aligned; tiny tiles keep cp.async
@@ -663,10 +663,11 @@ static bool make_tile_map(const SymParams& p, CUtensorMap* map) {
   if ((reinterpret_cast<uintptr_t>(p.in) & 15) || rs > 26) return false;
   const uint32_t bc_log = lc < 8 ? lc : 8;
   const cuuint64_t dims[3] = {8, (cuuint64_t)1 << rs, (cuuint64_t)(p.total >> rs)};
-  const cuuint64_t strides[2] = {sizeof(Fp), (cuuint64_t)sizeof(Fp) << rs};   // bytes, dimensions 1 and 2
+  // bytes, dimensions 1 and 2; a strided view (REDC reads every second element, src/fftree.rs:233) is a larger element pitch
+  const cuuint64_t strides[2] = {(cuuint64_t)sizeof(Fp) << p.in_shift, (cuuint64_t)sizeof(Fp) << (rs + p.in_shift)};
   const cuuint32_t box[3] = {4, 1u << bc_log, lc > 8 ? 1u : 1u << kr};
   const cuuint32_t estr[3] = {1, 1, 1};
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<Fp*>(p.in), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, const_cast<Fp*>(p.in + p.in_off), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
              CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
