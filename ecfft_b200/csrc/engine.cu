@@ -313,7 +313,7 @@ void Engine::enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, si
 // FFTree::redc_impl, src/fftree.rs:232-259, for nvec vectors of length len sharing `a`
 // (plain form).  a0inv (= 1/a[2i], plain) may be supplied when already known.
 void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out,
-                  const Fp* c_or_null, Fp* const* tabs_or_null, const ExitSplit* split) const {
+                  const Fp* c_or_null, Fp* const* tabs_or_null, const ExitSplit* split, const RedcChain* chain) const {
   const Level& lv = level_for(len);
   if (len < 2) throw Error(ERR_INVALID_ARG, "redc: length must be >= 2");
   const Fp* zinv = moiety == S0 ? lv.z0_inv_s1 : lv.z1_inv_s0;
@@ -347,8 +347,10 @@ void Engine::redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, s
       io2.E = split->evals; io2.e_shift = 1; io2.e_off = 0; io2.Z = split->xinv_even;
       io2.split = 1;
     }
-    const bool ok1 = k::extend_sym(lv.tw_d[moiety], lv.tw_r[other], lv.ctr[other], evals, out, log_h, nvec, P1, Kp, nullptr, st, &io1);
-    const bool ok2 = ok1 && k::extend_sym(lv.tw_d[other], lv.tw_r[moiety], lv.ctr[moiety], out, split ? split->next : out, log_h, nvec, lv.gami[other], lv.gam[moiety], nullptr, st, &io2);
+    const Fp* pre1 = chain && chain->pre_applied ? nullptr : P1;
+    const Fp* post2 = chain && chain->post_override ? chain->post_override : lv.gam[moiety];
+    const bool ok1 = k::extend_sym(lv.tw_d[moiety], lv.tw_r[other], lv.ctr[other], evals, out, log_h, nvec, pre1, Kp, nullptr, st, &io1);
+    const bool ok2 = ok1 && k::extend_sym(lv.tw_d[other], lv.tw_r[moiety], lv.ctr[moiety], out, split ? split->next : out, log_h, nvec, lv.gami[other], post2, nullptr, st, &io2);
     release(tabs);
     release(work);
     release(a0inv_own);
@@ -457,8 +459,11 @@ bool Engine::exit_tabs(const Level& lv) const {
     for (int i = 0; i < 3; i++) tab[r][i] = alloc(h);
     k::redc_tables(tab[r][0], tab[r][1], tab[r][2], lv.xnn_s, a0inv, lv.z0_inv_s1, lv.gami[S0], lv.gam[S1], r ? lv.z0z0 : nullptr, h, bs);
   }
+  Fp* post1 = alloc(h);
+  k::mul_strided(post1, lv.gam[S0], tab[1][0], 1, 0, h, bs);
   ECFFT_CUDA(cudaStreamSynchronize(bs));
   lv.exit_a0inv = a0inv;
+  lv.exit_post1 = post1;
   for (int r = 0; r < 2; r++)
     for (int i = 0; i < 3; i++) lv.exit_tab[r][i] = tab[r][i];
   return true;
@@ -475,17 +480,24 @@ bool Engine::exit_depths(Fp* cur, Fp* nxt, Fp* M, size_t len, size_t m_from, siz
     if (h >= 2 && (nvec * h) >= 4 && exit_tabs(lv)) {
       // MOD = REDC, x c, REDC (fftree.rs:277-281) with the level's prebuilt tables: four EXTENDs, no pointwise pass
       Fp* hb = tmp(m * nvec);
-      redc(cur, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, hb, nullptr, lv.exit_tab[0]);
+      // ECFFT_B200_NO_EXIT_CHAIN: REDC 2 applies its own pre-scale (A/B switch; chained: one product per element and depth fewer)
+      static const bool no_chain = getenv("ECFFT_B200_NO_EXIT_CHAIN") != nullptr;
+      RedcChain c1, c2;
+      if (!no_chain) {
+        c1.post_override = lv.exit_post1;
+        c2.pre_applied = true;
+      }
+      redc(cur, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, hb, nullptr, lv.exit_tab[0], nullptr, &c1);
       static const bool no_split = getenv("ECFFT_B200_NO_EXIT_SPLIT_FUSION") != nullptr;
       if (!no_split) {
         ExitSplit sp{cur, lv.exit_a0inv, nxt};
-        redc(hb, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, M, lv.z0z0, lv.exit_tab[1], &sp);   // ... and the split rides its last EXTEND
+        redc(hb, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, M, lv.z0z0, lv.exit_tab[1], &sp, &c2);   // ... and the split rides its last EXTEND
         release(hb);
         std::swap(cur, nxt);
         in_nxt = !in_nxt;
         continue;
       }
-      redc(hb, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, M, lv.z0z0, lv.exit_tab[1]);
+      redc(hb, lv.xnn_s, lv.exit_a0inv, m, nvec, S0, M, lv.z0z0, lv.exit_tab[1], nullptr, &c2);
       release(hb);
     } else {
       // the reference batch-inverts xnn_s[::2] on every call (fftree.rs:235); the stored xnn_s_inv holds the same values
@@ -589,6 +601,20 @@ void Engine::vanish(const Fp* domain, Fp* out, size_t n, DataForm form) const {
     const Level& lv = level_for(2 * len);
     if (!lv.z0_s1) throw Error(ERR_MISSING_TABLES, "vanish: tree was built without the Z tables");
     const size_t pairs = cnt / 2;
+    static const bool no_fuse = getenv("ECFFT_B200_NO_VANISH_FUSION") != nullptr;
+    if (!no_fuse && lv.sym && lv.has_norm() && k::butterfly_mode() == 2 && len >= 2 && len * pairs >= 4) {
+      // Fused form: the sibling products go straight to the even slots of the next array; MEXTEND reads them there as
+      // a stride-2 view and stores e + Z_0 into the odd slots (k_extend_sym's store epilogue): one pointwise pass and
+      // the EXTEND per depth instead of three passes and the EXTEND.
+      k::mul_pairs_even(Q2, Q, len, pairs, st);
+      k::SymIO io{1, 0, 1, 1, nullptr, 0, 0, lv.z0_s1, e};
+      if (!k::extend_sym(lv.tw_d[S0], lv.tw_r[S1], lv.ctr[S1], Q2, Q2, ilog2(len), pairs, lv.gami[S0], lv.gam[S1], nullptr, st, &io))
+        throw Error(ERR_INVALID_ARG, "vanish: fused MEXTEND refused an input it should take");
+      Fp* sw = Q;
+      Q = Q2;
+      Q2 = sw;
+      continue;
+    }
     k::mul_pairs(q0, Q, len, pairs, 0, st);
     k::extend(lv, q0, e, ilog2(len), pairs, S1, st);
     k::vanish_merge(Q2, q0, e, lv.z0_s1, fp_one(), len, pairs, st);

@@ -108,6 +108,7 @@ struct Level {
   // tables (kernels.cu redc_tables) depend on the level only and are built once, on first use (Engine::exit_tabs)
   mutable Fp* exit_tab[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};  // [redc 0 | redc 1 (x c)][P1, Kp, Zc], h each
   mutable Fp* exit_a0inv = nullptr;   // xnn_s_inv[::2], h
+  mutable Fp* exit_post1 = nullptr;   // gam[S0] * exit_tab[1][0]: REDC 1's last post-scale with REDC 2's first pre-scale folded in, h
   // ENTER with the next depth's pre-scale folded into this depth's combine (Engine::fold_tabs; built on first use, h each).
   // P = gami[0] of this level (the scale its input carries when "folded"), Pn = gami[0] of the level above (the scale
   // its output is to carry):  [0] gam[1][i] Pn[2i+1], [1] gx[i] Pn[2i+1]              (odd outputs, folded out)
@@ -276,6 +277,7 @@ void exit_split(Fp* next, const Fp* evals, const Fp* M, const Fp* xnn_inv, size_
 // VANISH pieces (fftree.rs:291-308)
 void vanish_base(Fp* out, const Fp* dom, Fp l0, Fp l1, size_t n, cudaStream_t st);            // out[2i] = a-l0, out[2i+1] = a-l1
 void mul_pairs(Fp* q0, const Fp* Q, size_t len, size_t npairs, int fix_mont, cudaStream_t st); // q0[w] = Q[2w]*Q[2w+1]
+void mul_pairs_even(Fp* out, const Fp* Q, size_t len, size_t npairs, cudaStream_t st);         // out[w][2i] = Q[2w][i]*Q[2w+1][i]
 void vanish_merge(Fp* out, const Fp* q0, const Fp* e, const Fp* z, Fp zscale, size_t len, size_t nvec, cudaStream_t st);
 // DEGREE pieces (fftree.rs:169-192)
 void count_neq(unsigned long long* counter, const Fp* a, const Fp* b, size_t n, cudaStream_t st);
@@ -319,8 +321,12 @@ struct Engine {
   // c_or_null: evals are to be multiplied pointwise by c first (MOD's middle step, folded into the tables)
   // EXIT (fftree.rs:206-220): the next depth's array [u0 | (e0 - u0) * xnn_inv[::2]] written by REDC's last EXTEND
   struct ExitSplit { const Fp* evals; const Fp* xinv_even; Fp* next; };
+  // Two REDCs in a row (MOD inside EXIT): the even outputs of the first feed nothing but the first EXTEND of the second,
+  // so its pre-scale rides the first one's last post-scale (post_override) and the second skips it (pre_applied).
+  struct RedcChain { const Fp* post_override = nullptr; bool pre_applied = false; };
   void redc(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, size_t len, size_t nvec, Moiety moiety, Fp* out,
-            const Fp* c_or_null = nullptr, Fp* const* tabs_or_null = nullptr, const ExitSplit* split = nullptr) const;  // tabs: prebuilt {P1, Kp, Zc} of the fused form
+            const Fp* c_or_null = nullptr, Fp* const* tabs_or_null = nullptr, const ExitSplit* split = nullptr,
+            const RedcChain* chain = nullptr) const;  // tabs: prebuilt {P1, Kp, Zc} of the fused form
   bool exit_tabs(const Level& lv) const;  // builds lv.exit_tab / exit_a0inv once; false: the fused REDC does not apply
   void modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, const Fp* c_plain, size_t len, size_t nvec, Fp* out) const;
 

@@ -288,6 +288,13 @@ void mul_pairs(Fp* q0, const Fp* Q, size_t len, size_t npairs, int fix_mont, cud
     fp_store(q0 + idx, r);
   });
 }
+// out[w][2i] = Q[2w][i] * Q[2w+1][i]: the sibling product written where VANISH's interleave wants it (src/fftree.rs:303-307)
+void mul_pairs_even(Fp* out, const Fp* Q, size_t len, size_t npairs, cudaStream_t st) {
+  map(len * npairs, st, [=] __device__(size_t idx) {
+    size_t w = idx / len, i = idx % len;
+    fp_store(out + w * 2 * len + 2 * i, fp_mul(fp_load(Q + 2 * w * len + i), fp_load(Q + (2 * w + 1) * len + i)));
+  });
+}
 // out[w][2i] = q0[w][i]; out[w][2i+1] = e[w][i] + z[i]*zscale
 void vanish_merge(Fp* out, const Fp* q0, const Fp* e, const Fp* z, Fp zscale, size_t len, size_t nvec, cudaStream_t st) {
   map(len * nvec, st, [=] __device__(size_t idx) {

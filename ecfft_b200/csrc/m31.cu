@@ -561,6 +561,13 @@ static Tree* build(size_t n, int device) {
   std::unique_ptr<Tree> t(new Tree());
   t->device = device;
   t->log_n = log_n;
+  {   // scratch comes from the stream-ordered pool: keep freed blocks instead of returning them to the driver at every sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      uint64_t thr = UINT64_MAX;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+  }
   ECFFT_CUDA(cudaStreamCreateWithFlags(&t->st, cudaStreamNonBlocking));
   // the chain of 2-isogenies that each lower the generator's order (src/ec.rs:523-543)
   F a = ca, b = cb;

@@ -396,6 +396,8 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
       }
       if (p.E)
         x = fp_dot2_lazy(FLOW ? fp_load_cg(p.E + ((g << p.e_shift) + p.e_off)) : fp_load(p.E + ((g << p.e_shift) + p.e_off)), fp_load_ro(p.Z + i), x, fp_load_ro(p.post + i));
+      else if (p.Z && p.post)   // MEXTEND inside VANISH (src/fftree.rs:133-134, 304): Z[i] + x * post[i], one reduction
+        x = fp_muladd_lazy(fp_load_ro(p.Z + i), x, fp_load_ro(p.post + i));
       else if (p.post)
         x = fp_mul_lazy(x, fp_load_ro(p.post + i));
       fp_store(p.out + ((g << p.out_shift) + p.out_off), fp_canon(x));
