@@ -522,7 +522,11 @@ void Engine::mextend(const Fp* in, Fp* out, size_t h, Moiety target, DataForm fo
   k::add_bcast_scaled(out, out, z, form == FORM_MONT ? fp_const_R() : fp_one(), h, 1, st);
 }
 
-// FFTree::degree_impl, src/fftree.rs:169-192
+// FFTree::degree_impl, src/fftree.rs:169-192.  The recursion follows ONE data-dependent branch per level (g1 == e1?).
+// With the symmetric tables the branch is taken on the device: the level's difference count stays in device memory,
+// one pointwise kernel does either side's pointwise step, and the second EXTEND is launched with that count as its
+// condition (k_extend_sym returns at once when it is zero) — no host round trip per level; the result is read back
+// once.  The last levels (fewer than 16 elements) and trees without those tables read the count back per level.
 size_t Engine::degree(const Fp* evals, size_t n) const {
   level_for(n);
   if (n == 1) return 0;
@@ -530,36 +534,58 @@ size_t Engine::degree(const Fp* evals, size_t n) const {
   Fp* e1 = tmp(n / 2);
   Fp* g1 = tmp(n / 2);
   Fp* curbuf = tmp(n);
-  unsigned long long* counter = nullptr;
-  ECFFT_CUDA(cudaMallocAsync((void**)&counter, sizeof(unsigned long long), st));
+  Fp* work = tmp(n / 2);
+  unsigned long long* counters = nullptr;   // [level] difference counts, [64] the degree accumulated on the device
+  ECFFT_CUDA(cudaMallocAsync((void**)&counters, 65 * sizeof(unsigned long long), st));
+  ECFFT_CUDA(cudaMemsetAsync(counters, 0, 65 * sizeof(unsigned long long), st));
+  static const bool host_branch = getenv("ECFFT_B200_DEGREE_HOST_BRANCH") != nullptr;
   const Fp* cur = evals;
   size_t len = n, result = 0;
+  uint32_t lvl = 0;
+  bool on_device = false;
   while (len > 1) {
     const Level& lv = level_for(len);
     if (!lv.z0_inv_s1) throw Error(ERR_MISSING_TABLES, "degree: tree was built without the Z tables");
     const size_t h = len / 2;
+    const uint32_t log_h = ilog2(h);
     k::deinterleave(e0, e1, cur, h, st);
-    k::extend(lv, e0, g1, ilog2(h), 1, S1, st);
-    ECFFT_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st));
-    k::count_neq(counter, g1, e1, h, st);
-    unsigned long long diff = 0;
-    ECFFT_CUDA(cudaMemcpyAsync(&diff, counter, sizeof diff, cudaMemcpyDeviceToHost, st));
-    ECFFT_CUDA(cudaStreamSynchronize(st));
-    if (diff == 0) {
-      ECFFT_CUDA(cudaMemcpyAsync(curbuf, e0, h * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+    k::extend(lv, e0, g1, log_h, 1, S1, st);
+    k::count_neq(counters + lvl, g1, e1, h, st);
+    if (!host_branch && h >= 8 && lv.sym && lv.has_norm() && k::butterfly_mode() == 2) {
+      k::degree_step(counters + lvl, e1, g1, lv.z0_inv_s1, e0, curbuf, h, counters + 64, st);
+      k::SymIO io{0, 0, 0, 0, nullptr, 0, 0, nullptr, work};
+      io.cond = counters + lvl;
+      if (!k::extend_sym(lv.tw_d[S1], lv.tw_r[S0], lv.ctr[S0], e1, curbuf, log_h, 1, lv.gami[S1], lv.gam[S0], nullptr, st, &io))
+        throw Error(ERR_INVALID_ARG, "degree: EXTEND refused an input it should take");
+      on_device = true;
     } else {
-      k::sub_mul_bcast(e1, e1, g1, lv.z0_inv_s1, h, 1, st);  // t1
-      k::extend(lv, e1, curbuf, ilog2(h), 1, S0, st);         // t0
-      result += h;
+      unsigned long long diff = 0;
+      ECFFT_CUDA(cudaMemcpyAsync(&diff, counters + lvl, sizeof diff, cudaMemcpyDeviceToHost, st));
+      ECFFT_CUDA(cudaStreamSynchronize(st));
+      if (diff == 0) {
+        ECFFT_CUDA(cudaMemcpyAsync(curbuf, e0, h * sizeof(Fp), cudaMemcpyDeviceToDevice, st));
+      } else {
+        k::sub_mul_bcast(e1, e1, g1, lv.z0_inv_s1, h, 1, st);  // t1
+        k::extend(lv, e1, curbuf, log_h, 1, S0, st);            // t0
+        result += h;
+      }
     }
     cur = curbuf;
     len = h;
+    lvl++;
+  }
+  if (on_device) {
+    unsigned long long dev_part = 0;
+    ECFFT_CUDA(cudaMemcpyAsync(&dev_part, counters + 64, sizeof dev_part, cudaMemcpyDeviceToHost, st));
+    ECFFT_CUDA(cudaStreamSynchronize(st));
+    result += (size_t)dev_part;
   }
   release(e0);
   release(e1);
   release(g1);
   release(curbuf);
-  ECFFT_CUDA(cudaFreeAsync(counter, st));
+  release(work);
+  ECFFT_CUDA(cudaFreeAsync(counters, st));
   return result;
 }
 

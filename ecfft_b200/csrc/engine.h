@@ -211,6 +211,7 @@ struct SymParams {
   // split != 0 (EXIT's last EXTEND of a depth, src/fftree.rs:206-220): u0 = x * post is stored at
   // out[(vector << (log_h + 1)) + i] and v0 = (E[(g << e_shift) + e_off] - u0) * Z[i] at the same place + h
   uint32_t split;
+  const unsigned long long* cond;   // not null: the whole pass is skipped when *cond == 0 (DEGREE's data-dependent branch, on the device)
   uint32_t tma_fence;
   uint32_t l2pf;              // strided tiles: bulk L2 prefetch of the tile's twiddle / combine-table ranges (set by launch_sym)
   uint32_t pf;                // twiddle prefetch ahead of each stage: 0 off, 1 into L1, 2 into L2 (set by launch_sym)
@@ -240,7 +241,8 @@ void flow_stats_read(unsigned long long out4[4]);    // {wait cycles, body cycle
 // Strided views for REDC (fftree.rs:232-259): logical element g is read at in[(g << in_shift) + in_off] and
 // written at out[(g << out_shift) + out_off]; with E the store is E[(g << e_shift) + e_off] * Z[i] + x * post[i]
 // (i = position within the vector).  work: contiguous scratch of nvec * h elements for multi-pass EXTENDs.
-struct SymIO { uint32_t in_shift, in_off, out_shift, out_off; const Fp* E; uint32_t e_shift, e_off; const Fp* Z; Fp* work; uint32_t split = 0; };
+struct SymIO { uint32_t in_shift, in_off, out_shift, out_off; const Fp* E; uint32_t e_shift, e_off; const Fp* Z; Fp* work; uint32_t split = 0;
+               const unsigned long long* cond = nullptr; };   // cond: every pass is skipped when *cond == 0
 bool extend_sym(const Fp* tw_d, const Fp* tw_r, const Fp* ctr, const Fp* in, Fp* out, uint32_t log_h, size_t nvec, const Fp* pre, const Fp* post,
                 const SymCombine* comb, cudaStream_t st, const SymIO* io = nullptr);
 void mg_cross(const Level& lv, int phase, uint32_t j, int role, size_t p_pos0, const Fp* own, const Fp* partner, size_t count, Fp* out, cudaStream_t st,
@@ -281,6 +283,9 @@ void mul_pairs_even(Fp* out, const Fp* Q, size_t len, size_t npairs, cudaStream_
 void vanish_merge(Fp* out, const Fp* q0, const Fp* e, const Fp* z, Fp zscale, size_t len, size_t nvec, cudaStream_t st);
 // DEGREE pieces (fftree.rs:169-192)
 void count_neq(unsigned long long* counter, const Fp* a, const Fp* b, size_t n, cudaStream_t st);
+// one level of DEGREE decided on the device (fftree.rs:181-191): *diff == 0: next = e0; else e1 = (e1 - g1) * zinv and *result += h
+void degree_step(const unsigned long long* diff, Fp* e1, const Fp* g1, const Fp* zinv, const Fp* e0, Fp* next, size_t h,
+                 unsigned long long* result, cudaStream_t st);
 void sub_mul_bcast(Fp* out, const Fp* a, const Fp* b, const Fp* c, size_t len, size_t nvec, cudaStream_t st);  // (a-b)*c
 // generic helpers
 void pow_u64(Fp* out, const Fp* in, uint64_t e, size_t n, cudaStream_t st);

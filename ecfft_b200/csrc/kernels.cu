@@ -308,6 +308,17 @@ void count_neq(unsigned long long* counter, const Fp* a, const Fp* b, size_t n, 
     if (!fp_eq(fp_load(a + i), fp_load(b + i))) atomicAdd(counter, 1ull);
   });
 }
+void degree_step(const unsigned long long* diff, Fp* e1, const Fp* g1, const Fp* zinv, const Fp* e0, Fp* next, size_t h,
+                 unsigned long long* result, cudaStream_t st) {
+  map(h, st, [=] __device__(size_t i) {
+    if (__ldcg(diff) == 0) {
+      fp_store(next + i, fp_load(e0 + i));
+    } else {
+      fp_store(e1 + i, fp_mul(fp_sub(fp_load(e1 + i), fp_load(g1 + i)), fp_load_ro(zinv + i)));
+      if (i == 0) atomicAdd(result, (unsigned long long)h);
+    }
+  });
+}
 void sub_mul_bcast(Fp* out, const Fp* a, const Fp* b, const Fp* c, size_t len, size_t nvec, cudaStream_t st) {
   map(len * nvec, st, [=] __device__(size_t i) {
     fp_store(out + i, fp_mul(fp_sub(fp_load(a + i), fp_load(b + i)), fp_load_ro(c + i % len)));

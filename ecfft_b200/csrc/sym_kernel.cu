@@ -439,6 +439,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym(const __grid_constant__
   // the prerequisite grid has completed and its memory is visible).  No-ops without the launch attribute.
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.cond && __ldcg(p.cond) == 0) return;
   if (p.packed)
     sym_tile<NT, false, false>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t);
   else
@@ -453,6 +454,7 @@ __global__ void __launch_bounds__(NT, MINB) k_extend_sym_tma(const __grid_consta
   __syncthreads();
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p.cond && __ldcg(p.cond) == 0) return;
   if (p.packed)
     sym_tile<NT, false, true>(p, smem_raw, 0, 0, (unsigned long long)blockIdx.x << p.log_t, &tmap, &mbar);
   else
@@ -773,6 +775,7 @@ bool plan_extend_sym(SymFlow& flow, const Fp* tw_d, const Fp* tw_r, const Fp* ct
   p.ctr = ctr;
   p.total = total;
   p.log_h = log_h;
+  p.cond = io ? io->cond : nullptr;
   if (comb) {
     p.A = comb->A;
     p.xnn = comb->xnn;

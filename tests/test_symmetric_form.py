@@ -117,3 +117,66 @@ def test_enter_with_fused_combine_constants(tree):
         cur = nxt
         m *= 2
     assert cur == O.from_mont(tree.enter(x))
+
+
+def test_enter_with_folded_prescale_tables(tree):
+    """Engine::enter_range_serial keeps the data between two depths multiplied by the NEXT depth's pre-scale
+    (P = 2^-L / Gamma^0 of the level that reads it) and carries the scale through the combine tables of
+    Level::fold_tab: odd {gam1 Pn[2i+1], gx Pn[2i+1]}, even folded->folded {Pn[2i]/P[i], xnn[2i] Pn[2i]/P[i]},
+    folded->plain {1/P[i], xnn[2i]/P[i]}, plain->folded {Pn[2i], xnn[2i] Pn[2i]}.  The EXTEND of a depth whose
+    input is folded skips its pre-scale.  Same result as the oracle's ENTER, wherever the range is cut."""
+    n = 64
+    x = O.random_elements(n, seed=7)
+    want = O.from_mont(tree.enter(x))
+
+    def prescale(t):   # what SymTables.extend applies first: 2^-L / Gamma^src, src = S0
+        inv2L = pow(2, -t.L, P)
+        return [inv2L * pow(t.gamma(0, p), -1, P) % P for p in range(t.h)]
+
+    def extend_unscaled_from_prescaled(t, v):   # SymTables.extend(target=1, scaled=False) minus its first line
+        h, L, src, target = t.h, t.L, 0, 1
+        v = list(v)
+        for j in range(L - 1, 0, -1):
+            for p in range(h):
+                if not (p >> j) & 1:
+                    q, gi = p + (1 << j), pow(t.g(src, j, p & ((1 << j) - 1)), -1, P)
+                    v[p], v[q] = (v[p] + v[q]) % P, (v[p] - v[q]) * gi % P
+        if L >= 1:
+            c = t.g(target, 0, 0) * pow(t.g(src, 0, 0), -1, P) % P
+            for p in range(0, h, 2):
+                s, tt = (v[p] + v[p + 1]) % P, c * (v[p] - v[p + 1]) % P
+                v[p], v[p + 1] = (s + tt) % P, (s - tt) % P
+        for j in range(1, L):
+            for p in range(h):
+                if not (p >> j) & 1:
+                    q, tt = p + (1 << j), t.g(target, j, p & ((1 << j) - 1)) * v[p + (1 << j)] % P
+                    v[p], v[q] = (v[p] + tt) % P, (v[p] - tt) % P
+        return v
+
+    for cuts in ([], [8], [2, 32]):                       # block sizes after which the data returns to plain form
+        cur, folded = O.from_mont(x), False
+        m = 2
+        while m <= n:
+            t, h = SymTables(tree, m), m // 2
+            Pm = prescale(t)
+            out_folded = m < n and m not in cuts
+            Pn = prescale(SymTables(tree, 2 * m)) if out_folded else None
+            gam1 = [t.gamma(1, i) for i in range(h)]
+            gx = [gam1[i] * t.xnn[2 * i + 1] % P for i in range(h)]
+            nxt = []
+            for off in range(0, n, m):
+                u0, v0 = cur[off:off + h], cur[off + h:off + m]
+                pu = u0 if folded else [a * b % P for a, b in zip(u0, Pm)]
+                pv = v0 if folded else [a * b % P for a, b in zip(v0, Pm)]
+                u1, v1 = extend_unscaled_from_prescaled(t, pu), extend_unscaled_from_prescaled(t, pv)
+                blk = [0] * m
+                for i in range(h):
+                    e0 = (pow(Pm[i], -1, P) if folded else 1) * (Pn[2 * i] if out_folded else 1) % P
+                    e1 = e0 * t.xnn[2 * i] % P
+                    so = Pn[2 * i + 1] if out_folded else 1
+                    blk[2 * i] = (e0 * u0[i] + e1 * v0[i]) % P
+                    blk[2 * i + 1] = (gam1[i] * so * u1[i] + gx[i] * so * v1[i]) % P
+                nxt += blk
+            cur, folded = nxt, out_folded
+            m *= 2
+        assert cur == want, cuts
