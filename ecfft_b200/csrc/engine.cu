@@ -118,7 +118,7 @@ static bool fold_enabled() {
   }
   return v != 0;
 }
-void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const {
+void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, int streams_hint) const {
   // n is any whole number of m_hi-blocks (the blocks are independent): a power of two for a full ENTER
   if (!is_pow2(m_lo) || !is_pow2(m_hi)) throw Error(ERR_NOT_POW2, "length is not a power of two");
   if (n == 0 || m_hi > n || m_lo > m_hi || n % m_hi) throw Error(ERR_INVALID_ARG, "enter: bad level range");
@@ -130,7 +130,9 @@ void Engine::enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_
   if (enter_range_flow(in, out, n, m_lo, m_hi)) return;
   // Independent ranges on concurrent streams: range s runs the depths up to m_mid (the largest block size
   // that tiles a range) on stream s, the caller's stream joins them and runs the remaining depths.
-  const int S = enter_streams(n);
+  // streams_hint: the caller's measured choice where the automatic one does not apply (the rank-local ENTER of the
+  // sharded schedule, whose launches are followed by flag waits instead of the next call's work); the environment wins
+  const int S = (streams_hint > 0 && getenv("ECFFT_B200_ENTER_STREAMS") == nullptr) ? streams_hint : enter_streams(n);
   if (S > 1 && !prof::enabled() && n % (size_t)S == 0 && n / (size_t)S >= enter_fork_min()) {
     const size_t part = n / (size_t)S;
     size_t m_mid = m_hi;

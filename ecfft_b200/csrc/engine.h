@@ -336,7 +336,7 @@ struct Engine {
   void modular_reduce(const Fp* evals, const Fp* a_plain, const Fp* a0inv_or_null, const Fp* c_plain, size_t len, size_t nvec, Fp* out) const;
 
   // the FFTree<F> surface (fftree.rs:72-316) on device buffers
-  void enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi) const;  // bottom-up levels m_lo < m <= m_hi
+  void enter_range(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, int streams_hint = 0) const;  // bottom-up levels m_lo < m <= m_hi
   // ... on this engine's stream only.  in_folded / out_folded: the input already carries / the output is to carry the
   // pre-scale of the EXTEND that consumes it next (the data between two depths of one ENTER)
   void enter_range_serial(const Fp* in, Fp* out, size_t n, size_t m_lo, size_t m_hi, bool in_folded = false, bool out_folded = false) const;
