@@ -79,14 +79,34 @@ static inline unsigned grid_for(size_t n, int threads) {
 
 template <class F>
 __global__ void __launch_bounds__(256) k_map(size_t n, F f) {
+  // programmatic dependent launch, as in k_extend_sym: the next kernel of the stream may be scheduled while this grid
+  // drains, and this one waits here for its own predecessor's results (no-ops without the launch attribute)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f(i);
+}
+static bool map_pdl() {   // ECFFT_B200_PDL (default 1), the knob of sym_kernel.cu
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_PDL");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
 }
 template <class F>
 static void map(size_t n, cudaStream_t st, F f) {
   if (n == 0) return;
-  k_map<<<grid_for(n, 256), 256, 0, st>>>(n, f);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid_for(n, 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = map_pdl() ? 1 : 0;
+  ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k_map<F>, n, f));
   prof::count_launch();
-  ECFFT_CUDA(cudaGetLastError());
 }
 
 // ------------------------------------------------------------------------------------------

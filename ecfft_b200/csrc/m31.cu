@@ -50,6 +50,8 @@ __host__ __device__ inline F finv(F x) { return fpow(x, P31 - 2); }   // 0 -> 0 
 // ---------------------------------------------------------------------------------------------------------
 template <class Fn>
 __global__ void k31_map(size_t n, Fn fn) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch, see k_extend_sym
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) fn(i);
 }
 template <class Fn>
@@ -57,9 +59,17 @@ static void map(size_t n, cudaStream_t st, Fn fn) {
   if (!n) return;
   size_t blocks = (n + 255) / 256;
   if (blocks > 148u * 16u) blocks = 148u * 16u;
-  k31_map<<<(unsigned)blocks, 256, 0, st>>>(n, fn);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)blocks);
+  cfg.blockDim = dim3(256);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k31_map<Fn>, n, fn));
   prof::count_launch();
-  ECFFT_CUDA(cudaGetLastError());
 }
 
 static constexpr uint32_t LT = 12;   // log2 tile elements
@@ -77,6 +87,8 @@ struct Pass {
 // half-strides 2^(lvl_hi-1) .. 2^lvl_lo, then recombine levels back up), in place in shared memory.
 __global__ void __launch_bounds__(256) k31_extend(const __grid_constant__ Pass p) {
   extern __shared__ F tile[];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t T = 1u << p.log_t;
   // tile element e -> global element and position within its vector
   unsigned long long gbase;
@@ -200,9 +212,18 @@ struct Eng {
 
   void launch(const Pass& p) {
     const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
-    k31_extend<<<(unsigned)tiles, 256, sizeof(F) << p.log_t, st>>>(p);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)tiles);
+    cfg.blockDim = dim3(256);
+    cfg.dynamicSmemBytes = sizeof(F) << p.log_t;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k31_extend, p));
     prof::count_launch();
-    ECFFT_CUDA(cudaGetLastError());
   }
   // EXTEND of nvec contiguous vectors of length h = 2^log_h towards `target` (src/fftree.rs:72-126); in may equal out
   void extend(const F* in, F* out, uint32_t log_h, size_t nvec, int target) {
