@@ -104,6 +104,9 @@ static void map(size_t n, cudaStream_t st, F f) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
+  // on every launch, like k_extend_sym's (ENTER -> EXIT at 2^12: 1.88 -> 1.79 ms, EXIT 2^22 30.84 -> 30.52 ms,
+  // profiles/r02_z_ab_pdl.txt).  Attaching it to some launches of a stream and not to others measured worst on the m31
+  // kernels (m31.cu pdl_mode), so there is no per-grid rule here.
   cfg.numAttrs = map_pdl() ? 1 : 0;
   ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k_map<F>, n, f));
   prof::count_launch();

@@ -54,6 +54,21 @@ __global__ void k31_map(size_t n, Fn fn) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) fn(i);
 }
+// Programmatic dependent launch is decided per CALL, for all of its launches: measured (profiles/r02_ab_m31_pdl.txt) it
+// gains 15-20 % at n = 2^16 (launch gaps dominate), is mixed at 2^20 and loses at 2^22 (the next grid's early-resident CTAs
+// take slots from the running one); attaching it to some launches of a call and not to others is the worst of all
+// (EXIT 2^22: 7.9 ms without, 8.9 ms on every launch, 10.6 ms on the small grids only).
+// ECFFT_B200_M31_PDL: 0 = never, 1 = calls of at most 2^20 elements (default), 2 = always.
+static int pdl_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_M31_PDL");
+    v = e ? atoi(e) : 1;
+  }
+  return v;
+}
+static thread_local bool t_pdl = false;   // set by the entry point for the call it runs
+static void set_call_size(size_t n) { t_pdl = pdl_mode() == 2 || (pdl_mode() == 1 && n <= ((size_t)1 << 20)); }
 template <class Fn>
 static void map(size_t n, cudaStream_t st, Fn fn) {
   if (!n) return;
@@ -67,7 +82,7 @@ static void map(size_t n, cudaStream_t st, Fn fn) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = t_pdl ? 1 : 0;
   ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k31_map<Fn>, n, fn));
   prof::count_launch();
 }
@@ -78,6 +93,10 @@ struct Pass {
   F* out;
   const uint4* dmat;
   const uint4* rmat;
+  const F* tw_d;    // symmetric form: 1/g of the source moiety, entry 2^j + i
+  const F* tw_r;    // symmetric form: g of the target moiety
+  const F* pre;     // per-position scale applied as the tile is loaded (or null)
+  const F* post;    // per-position scale applied as the tile is stored (or null)
   unsigned long long total, nv;
   uint32_t log_h, lvl_lo, lvl_hi, do_d, do_r, dskip, rskip;
   uint32_t packed, log_t, log_c, krows, row_shift;
@@ -85,6 +104,12 @@ struct Pass {
 
 // One pass of EXTEND on a tile (flattening of extend_impl, src/fftree.rs:72-120: decompose levels with
 // half-strides 2^(lvl_hi-1) .. 2^lvl_lo, then recombine levels back up), in place in shared memory.
+// SYM = false: the reference's 2x2 matrices (src/utils.rs:338-347), four products per pair.
+// SYM = true: the one-product butterflies of DESIGN.md 4.1 — every map of the m31 chain is, in the coordinate
+// y = x - x0, y + t/y + x0 with t a square (src/ec.rs:231-232), so the two nodes of a pair are y and beta^2/y and
+// g = (y - beta)/(y + beta) takes opposite values on them: recombine y_p = x_p + g x_q, y_q = x_p - g x_q, decompose
+// x_p = y_p + y_q, x_q = (y_p - y_q)/g, the diagonal scalings collected into one pre- and one post-scale.
+template <bool SYM>
 __global__ void __launch_bounds__(256) k31_extend(const __grid_constant__ Pass p) {
   extern __shared__ F tile[];
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -104,12 +129,14 @@ __global__ void __launch_bounds__(256) k31_extend(const __grid_constant__ Pass p
   auto goff = [&](uint32_t e) -> unsigned long long {
     return p.packed ? e : ((unsigned long long)(e >> p.log_c) << p.row_shift) + (e & ((1u << p.log_c) - 1));
   };
+  const uint32_t hmask = (1u << p.log_h) - 1;
   for (uint32_t e = threadIdx.x; e < T; e += blockDim.x) {
     const unsigned long long g = gbase + goff(e);
-    tile[e] = g < p.total ? p.in[g] : 0;
+    F v = g < p.total ? p.in[g] : 0;
+    if (SYM && p.pre) v = fmul(v, __ldg(p.pre + (uint32_t)(g & hmask)));
+    tile[e] = v;
   }
   __syncthreads();
-  const uint32_t hmask = (1u << p.log_h) - 1;
   const uint32_t boff = p.packed ? 0u : p.log_c - p.row_shift;   // tile bit of level j is j + boff (mod 2^32)
   for (int phase = 0; phase < 2; phase++) {
     if (phase == 0 ? !p.do_d : !p.do_r) continue;
@@ -117,20 +144,36 @@ __global__ void __launch_bounds__(256) k31_extend(const __grid_constant__ Pass p
       const uint32_t j = phase == 0 ? p.lvl_hi - 1 - s : p.lvl_lo + s;
       const uint32_t b = j + boff, S = 1u << b;
       const uint4* mats = (phase == 0 ? p.dmat : p.rmat) + (2u << j) + (phase == 0 ? p.dskip : p.rskip);
+      const F* tw = (phase == 0 ? p.tw_d : p.tw_r) + (1u << j);
       for (uint32_t q = threadIdx.x; q < T / 2; q += blockDim.x) {
         const uint32_t e0 = ((q >> b) << (b + 1)) | (q & (S - 1)), e1 = e0 + S;
-        const uint32_t pos = (uint32_t)((pos0 + goff(e0)) & hmask);
-        const uint4 m = __ldg(mats + 2 * (pos & ((1u << j) - 1)));
+        const uint32_t i = (uint32_t)((pos0 + goff(e0)) & hmask) & ((1u << j) - 1);
         const F x = tile[e0], y = tile[e1];
-        tile[e0] = fdot2(m.x, x, m.y, y);
-        tile[e1] = fdot2(m.z, x, m.w, y);
+        if (SYM) {
+          const F g = __ldg(tw + i);
+          if (phase == 0) {
+            tile[e0] = fadd(x, y);
+            tile[e1] = fmul(fsub(x, y), g);
+          } else {
+            const F t = fmul(g, y);
+            tile[e0] = fadd(x, t);
+            tile[e1] = fsub(x, t);
+          }
+        } else {
+          const uint4 m = __ldg(mats + 2 * i);
+          tile[e0] = fdot2(m.x, x, m.y, y);
+          tile[e1] = fdot2(m.z, x, m.w, y);
+        }
       }
       __syncthreads();
     }
   }
   for (uint32_t e = threadIdx.x; e < T; e += blockDim.x) {
     const unsigned long long g = gbase + goff(e);
-    if (g < p.total) p.out[g] = tile[e];
+    if (g >= p.total) continue;
+    F v = tile[e];
+    if (SYM && p.post) v = fmul(v, __ldg(p.post + (uint32_t)(g & hmask)));
+    p.out[g] = v;
   }
 }
 
@@ -142,6 +185,11 @@ struct Lv {
   uint4 *rmat = nullptr, *dmat = nullptr;                                   // N each
   F *xnn = nullptr, *xnn_inv = nullptr, *z0z0 = nullptr, *z1z1 = nullptr;   // N each
   F *z0_s1 = nullptr, *z1_s0 = nullptr, *z0i = nullptr, *z1i = nullptr;     // N/2 each
+  // symmetric-butterfly tables (h = N/2 entries each, index = moiety): g and 1/g at entry 2^j + i, the accumulated scale
+  // Gamma_p = prod_j (y_j(p) + beta_j) y_j(p)^(2^j - 1) and the pre-scale 2^-L / Gamma_p, and gam[1][i] * xnn[2i+1]
+  bool sym = false;
+  F *tw_r[2] = {nullptr, nullptr}, *tw_d[2] = {nullptr, nullptr}, *gam[2] = {nullptr, nullptr}, *gami[2] = {nullptr, nullptr};
+  F* gx = nullptr;
 };
 struct Map { F x0, t; };   // r(x) = (x^2 - x0 x + t) / (x - x0), src/ec.rs:231-232
 
@@ -210,7 +258,7 @@ struct Eng {
     return t.lv[lg];
   }
 
-  void launch(const Pass& p) {
+  void launch(const Pass& p, bool sym) {
     const size_t tiles = (p.total + ((size_t)1 << p.log_t) - 1) >> p.log_t;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)tiles);
@@ -221,21 +269,30 @@ struct Eng {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k31_extend, p));
+    cfg.numAttrs = t_pdl ? 1 : 0;   // see pdl_mode()
+    if (sym) ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k31_extend<true>, p));
+    else ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k31_extend<false>, p));
     prof::count_launch();
   }
-  // EXTEND of nvec contiguous vectors of length h = 2^log_h towards `target` (src/fftree.rs:72-126); in may equal out
-  void extend(const F* in, F* out, uint32_t log_h, size_t nvec, int target) {
+  // EXTEND of nvec contiguous vectors of length h = 2^log_h towards `target` (src/fftree.rs:72-126); in may equal out.
+  // unscaled: with the symmetric tables, leave the final Gamma^target scaling to the caller (ENTER's combine carries it).
+  void extend(const F* in, F* out, uint32_t log_h, size_t nvec, int target, bool unscaled = false) {
     const Lv& lv = level_for((size_t)2 << log_h);
     const size_t total = nvec << log_h;
     if (log_h == 0) {
       if (in != out) ECFFT_CUDA(cudaMemcpyAsync(out, in, total * sizeof(F), cudaMemcpyDeviceToDevice, st));
       return;
     }
+    static const bool force_matrix = getenv("ECFFT_B200_M31_MATRIX") != nullptr;   // A/B switch: the reference's matrix butterflies
+    const bool sym = lv.sym && !force_matrix;
+    if (unscaled && !sym) throw Error(ERR_INVALID_ARG, "m31 extend: unscaled output needs the symmetric tables");
     Pass p{};
     p.dmat = lv.dmat;
     p.rmat = lv.rmat;
+    p.tw_d = sym ? lv.tw_d[1 - target] : nullptr;
+    p.tw_r = sym ? lv.tw_r[target] : nullptr;
+    const F* pre = sym ? lv.gami[1 - target] : nullptr;
+    const F* post = (sym && !unscaled) ? lv.gam[target] : nullptr;
     p.total = total;
     p.log_h = log_h;
     p.dskip = target == 0 ? 1 : 0;   // src/fftree.rs:87-90
@@ -243,7 +300,8 @@ struct Eng {
     p.log_t = LT;
     if (log_h <= LT) {               // whole vectors per tile: one launch
       p.in = in; p.out = out; p.packed = 1; p.lvl_lo = 0; p.lvl_hi = log_h; p.do_d = p.do_r = 1; p.nv = 1;
-      launch(p);
+      p.pre = pre; p.post = post;
+      launch(p, sym);
       return;
     }
     const uint32_t outer = log_h - LT, kmax = LT - 7, npass = (outer + kmax - 1) / kmax;
@@ -255,16 +313,19 @@ struct Eng {
       p.in = src; p.out = out; p.packed = 0; p.do_d = 1; p.do_r = 0;
       p.lvl_hi = bounds[i]; p.lvl_lo = bounds[i + 1];
       p.krows = p.lvl_hi - p.lvl_lo; p.log_c = LT - p.krows; p.row_shift = p.lvl_lo;
-      launch(p);
+      p.pre = i == 0 ? pre : nullptr; p.post = nullptr;
+      launch(p, sym);
       src = out;
     }
     p.in = src; p.out = out; p.packed = 1; p.lvl_lo = 0; p.lvl_hi = LT; p.do_d = p.do_r = 1;
-    launch(p);
+    p.pre = nullptr; p.post = nullptr;
+    launch(p, sym);
     for (uint32_t i = npass; i-- > 0;) {     // outer recombine passes, top levels last
       p.in = out; p.out = out; p.packed = 0; p.do_d = 0; p.do_r = 1;
       p.lvl_hi = bounds[i]; p.lvl_lo = bounds[i + 1];
       p.krows = p.lvl_hi - p.lvl_lo; p.log_c = LT - p.krows; p.row_shift = p.lvl_lo;
-      launch(p);
+      p.pre = nullptr; p.post = i == 0 ? post : nullptr;
+      launch(p, sym);
     }
   }
 
@@ -284,14 +345,25 @@ struct Eng {
       const size_t h = m / 2;
       const uint32_t log_h = ilog2(h);
       F* dst = m == n ? out : ping[idx & 1];
-      extend(cur, W, log_h, n / h, 1);
+      static const bool force_matrix = getenv("ECFFT_B200_M31_MATRIX") != nullptr;
+      const bool sym = lv.sym && !force_matrix && log_h >= 1;
+      extend(cur, W, log_h, n / h, 1, sym);
       const F* A = cur;
       const F* xnn = lv.xnn;
-      map(n / 2, st, [=] __device__(size_t k) {
-        const size_t blk = k >> log_h, i = k & (h - 1), off = blk << (log_h + 1);
-        dst[off + 2 * i] = fadd(A[off + i], fmul(A[off + h + i], __ldg(xnn + 2 * i)));
-        dst[off + 2 * i + 1] = fadd(W[off + i], fmul(W[off + h + i], __ldg(xnn + 2 * i + 1)));
-      });
+      if (sym) {   // the EXTEND left out its Gamma^1 scaling: out[2i+1] = gam1[i] u1^ + (gam1[i] xnn[2i+1]) v1^, one reduction
+        const F *gam1 = lv.gam[1], *gx = lv.gx;
+        map(n / 2, st, [=] __device__(size_t k) {
+          const size_t blk = k >> log_h, i = k & (h - 1), off = blk << (log_h + 1);
+          dst[off + 2 * i] = fadd(A[off + i], fmul(A[off + h + i], __ldg(xnn + 2 * i)));
+          dst[off + 2 * i + 1] = fdot2(__ldg(gam1 + i), W[off + i], __ldg(gx + i), W[off + h + i]);
+        });
+      } else {
+        map(n / 2, st, [=] __device__(size_t k) {
+          const size_t blk = k >> log_h, i = k & (h - 1), off = blk << (log_h + 1);
+          dst[off + 2 * i] = fadd(A[off + i], fmul(A[off + h + i], __ldg(xnn + 2 * i)));
+          dst[off + 2 * i + 1] = fadd(W[off + i], fmul(W[off + h + i], __ldg(xnn + 2 * i + 1)));
+        });
+      }
       cur = dst;
     }
   }
@@ -575,6 +647,7 @@ static Tree* build(size_t n, int device) {
   Pt g{1273083559u, 804329170u, false};
   const uint32_t two_adic = 28;
   if (!is_pow2(n)) throw Error(ERR_NOT_POW2, "n is not a power of two");
+  t_pdl = false;
   const uint32_t log_n = ilog2(n);
   if (log_n > two_adic) throw Error(ERR_TOO_LARGE, "FFTree size is too large for the generator (log2 n > 28)");   // src/ec.rs:513-515
   for (uint32_t i = 0; i < two_adic - log_n; i++) g = padd(g, g, ca, cb);
@@ -671,6 +744,61 @@ static Tree* build(size_t n, int device) {
   return t.release();
 }
 
+// Symmetric-butterfly tables of the chain level with N = 2^k leaves: the level with half-stride 2^j
+// uses the level's f layer with 2^(j+2) nodes and that layer's map (x0_j, t_j = beta_j^2).
+static void build_sym_tables(Tree& t, uint32_t k) {
+  Lv& lv = t.lv[k];
+  if (k < 2) return;
+  const uint32_t L = k - 1;
+  const size_t n = t.n(), N = (size_t)1 << k, stride = n / N, h = N / 2;
+  std::vector<F> host(2 * L);
+  for (uint32_t j = 0; j < L; j++) {
+    const Map& m = t.maps[k - 2 - j];
+    const F beta = fpow(m.t, ((uint64_t)P31 + 1) / 4);   // p = 3 (mod 4)
+    if (fmul(beta, beta) != m.t) return;                  // t is not a square: keep the matrix butterflies for this level
+    host[2 * j] = m.x0;
+    host[2 * j + 1] = beta;
+  }
+  cudaStream_t st = t.st;
+  F* xb = t.alloc<F>(2 * L);
+  ECFFT_CUDA(cudaMemcpyAsync(xb, host.data(), 2 * L * sizeof(F), cudaMemcpyHostToDevice, st));
+  ECFFT_CUDA(cudaStreamSynchronize(st));
+  const F* f = t.f;
+  F inv2L = 1;
+  for (uint32_t j = 0; j < L; j++) inv2L = fmul(inv2L, (P31 + 1) / 2);
+  for (int mu = 0; mu < 2; mu++) {
+    F *twr = lv.tw_r[mu] = t.alloc<F>(h), *twd = lv.tw_d[mu] = t.alloc<F>(h);
+    F *gam = lv.gam[mu] = t.alloc<F>(h), *gami = lv.gami[mu] = t.alloc<F>(h);
+    map(h, st, [=] __device__(size_t idx) {
+      if (idx == 0) { twr[0] = twd[0] = 0; return; }
+      const uint32_t j = 31 - __clz((unsigned)idx);
+      const size_t i = idx - ((size_t)1 << j);
+      const F* layer = f + (n >> (k - 2 - j));
+      const F y0 = fsub(layer[(2 * i + mu) * stride], xb[2 * j]), beta = xb[2 * j + 1];
+      const F num = fsub(y0, beta), den = fadd(y0, beta);
+      twr[idx] = fmul(num, finv(den));
+      twd[idx] = fmul(den, finv(num));
+    });
+    map(h, st, [=] __device__(size_t pp) {
+      F acc = 1;
+      for (uint32_t j = 0; j < L; j++) {
+        const size_t i = pp & (((size_t)1 << j) - 1), bit = (pp >> j) & 1;
+        const F* layer = f + (n >> (k - 2 - j));
+        const F y = fsub(layer[(2 * i + mu + bit * ((size_t)2 << j)) * stride], xb[2 * j]);
+        acc = fmul(acc, fmul(fadd(y, xb[2 * j + 1]), fpow(y, ((uint64_t)1 << j) - 1)));
+      }
+      gam[pp] = acc;
+      gami[pp] = fmul(inv2L, finv(acc));
+    });
+  }
+  {
+    F* gx = lv.gx = t.alloc<F>(h);
+    const F *gam1 = lv.gam[1], *xnn = lv.xnn;
+    map(h, st, [=] __device__(size_t i) { gx[i] = fmul(gam1[i], xnn[2 * i + 1]); });
+  }
+  lv.sym = true;
+}
+
 // from_tree (src/fftree.rs:318-463) for the chain level with N = 2^k leaves = every (n/N)-th leaf of the top tree;
 // the levels below are complete (the reference derives the subtree first, :319).
 static void build_level(Tree& t, uint32_t k, Eng& eng) {
@@ -717,6 +845,7 @@ static void build_level(Tree& t, uint32_t k, Eng& eng) {
     });
   }
   if (k == 0) return;
+  build_sym_tables(t, k);   // from here on this level's EXTENDs run the one-product butterflies
   lv.z0_s1 = t.alloc<F>(h);
   lv.z1_s0 = t.alloc<F>(h);
   lv.z0i = t.alloc<F>(h);
@@ -860,6 +989,7 @@ struct Io {
 #define M31_LOCKED                                                   \
   need(t != nullptr, ERR_INVALID_ARG, "null tree handle");           \
   std::lock_guard<std::mutex> lock(const_cast<ecfft_m31_tree*>(t)->mu); \
+  m31::set_call_size(n);                                             \
   Io io(t);
 
 extern "C" {
@@ -879,9 +1009,10 @@ size_t ecfft_m31_tree_leaves(const ecfft_m31_tree* t) { return t ? t->n() : 0; }
 int ecfft_m31_tree_table(const ecfft_m31_tree* t, size_t subtree_leaves, const char* name, uint32_t* out, size_t cap, size_t* count) {
   return guard31([&] {
     need(t && name && count, ERR_INVALID_ARG, "null argument");
+    const size_t n = subtree_leaves;
     M31_LOCKED
     const m31::Lv& lv = io.eng.level_for(subtree_leaves);
-    const size_t N = subtree_leaves, h = N / 2, n = t->n();
+    const size_t N = subtree_leaves, h = N / 2, n_top = t->n();
     const std::string nm(name);
     const void* src = nullptr;
     size_t cnt = 0;
@@ -891,10 +1022,10 @@ int ecfft_m31_tree_table(const ecfft_m31_tree* t, size_t subtree_leaves, const c
       staged = io.eng.tmp(cnt);
       ECFFT_CUDA(cudaMemsetAsync(staged, 0, sizeof(m31::F), t->st));
       const m31::F* f = t->f;
-      const size_t stride = n / N;
+      const size_t stride = n_top / N;
       for (uint32_t kk = 0; kk <= lv.log_n; kk++) {
         m31::F* dst = staged + (N >> kk);
-        const m31::F* s = f + (n >> kk);
+        const m31::F* s = f + (n_top >> kk);
         m31::map(N >> kk, t->st, [=] __device__(size_t i) { dst[i] = s[i * stride]; });
       }
       src = staged;
@@ -1012,6 +1143,7 @@ int ecfft_m31_enter_dev(const ecfft_m31_tree* t, const void* coeffs, size_t n, v
   return guard31([&] {
     need(t && coeffs && evals, ERR_INVALID_ARG, "null argument");
     DeviceGuard g(t->device);
+    m31::set_call_size(n);
     m31::Eng eng(*t, (cudaStream_t)stream);
     eng.enter((const m31::F*)coeffs, (m31::F*)evals, n);
   });
@@ -1020,6 +1152,7 @@ int ecfft_m31_exit_dev(const ecfft_m31_tree* t, const void* evals, size_t n, voi
   return guard31([&] {
     need(t && coeffs && evals, ERR_INVALID_ARG, "null argument");
     DeviceGuard g(t->device);
+    m31::set_call_size(n);
     m31::Eng eng(*t, (cudaStream_t)stream);
     eng.exit((const m31::F*)evals, (m31::F*)coeffs, n);
   });
@@ -1030,6 +1163,7 @@ int ecfft_m31_extend_dev(const ecfft_m31_tree* t, const void* evals, size_t n, i
     need(moiety == 0 || moiety == 1, ERR_INVALID_ARG, "bad moiety");
     need(n > 0 && n <= ((size_t)1 << 30), ERR_NOT_POW2, "bad length");
     DeviceGuard g(t->device);
+    m31::set_call_size(n);
     m31::Eng eng(*t, (cudaStream_t)stream);
     eng.level_for(2 * n);
     eng.extend((const m31::F*)evals, (m31::F*)out, m31::ilog2(n), 1, moiety);

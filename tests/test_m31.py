@@ -70,6 +70,58 @@ def test_reference_definitions(ref64):
     assert len(M.cubic_roots(M.CURVE_A, M.CURVE_B)) >= 1
 
 
+def test_symmetric_butterflies_equal_the_matrix_network(ref64):
+    """The one-product butterflies of m31.cu (k31_extend<true>): in the coordinate y = x - x0 every map of the chain is
+    y + t/y + x0 with t a square, so the two nodes of a pair are y and beta^2/y and g = (y - beta)/(y + beta) takes
+    opposite values on them; EXTEND = Gamma^tgt . prod [[1, g],[1, -g]] . prod ([[1, g],[1, -g]]^src)^-1 . 2^-L / Gamma^src
+    with Gamma_p = prod_j (y_j(p) + beta_j) y_j(p)^(2^j - 1) — bit-identical to the reference's 2x2 matrix network."""
+    rng = random.Random(3)
+
+    def sqrt_p(a):
+        r = pow(a, (P + 1) // 4, P)
+        assert r * r % P == a % P, "t must be a square for the symmetric form"
+        return r
+
+    for N in (4, 8, 64):
+        t = ref64.subtree_with_size(N)
+        h, L, logN = N // 2, (N // 2).bit_length() - 1, N.bit_length() - 1
+        x0 = [(-t.maps[logN - 2 - j][1][0]) % P for j in range(L)]
+        beta = [sqrt_p(t.maps[logN - 2 - j][0][0]) for j in range(L)]
+
+        def y(mu, j, i, bit):
+            return (t.f[(4 << j) + 2 * i + mu + bit * (2 << j)] - x0[j]) % P
+
+        def g(mu, j, i):
+            return (y(mu, j, i, 0) - beta[j]) * pow(y(mu, j, i, 0) + beta[j], -1, P) % P
+
+        def gamma(mu, p):
+            acc = 1
+            for j in range(L):
+                yy = y(mu, j, p & ((1 << j) - 1), (p >> j) & 1)
+                acc = acc * (yy + beta[j]) * pow(yy, (1 << j) - 1, P) % P
+            return acc
+
+        for mu in (0, 1):
+            for j in range(L):
+                for i in range(1 << j):
+                    assert y(mu, j, i, 0) * y(mu, j, i, 1) % P == beta[j] ** 2 % P
+        x = [rng.randrange(P) for _ in range(h)]
+        for target in (0, 1):
+            src = 1 - target
+            v = [xi * pow(2, -L, P) * pow(gamma(src, p), -1, P) % P for p, xi in enumerate(x)]
+            for j in range(L - 1, -1, -1):
+                for p in range(h):
+                    if not (p >> j) & 1:
+                        q, gi = p + (1 << j), pow(g(src, j, p & ((1 << j) - 1)), -1, P)
+                        v[p], v[q] = (v[p] + v[q]) % P, (v[p] - v[q]) * gi % P
+            for j in range(L):
+                for p in range(h):
+                    if not (p >> j) & 1:
+                        q, tt = p + (1 << j), g(target, j, p & ((1 << j) - 1)) * v[p + (1 << j)] % P
+                        v[p], v[q] = (v[p] + tt) % P, (v[p] - tt) % P
+            assert [vi * gamma(target, p) % P for p, vi in enumerate(v)] == t.extend(x, target), (N, target)
+
+
 def test_chain_constants():
     """src/lib.rs:199-206: both points are on y^2 = x^3 + x and the generator has order exactly 2^28"""
     for (x, y) in (M.COSET_OFFSET, M.SUBGROUP_GENERATOR):
