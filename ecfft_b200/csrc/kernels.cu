@@ -85,11 +85,14 @@ __global__ void __launch_bounds__(256) k_map(size_t n, F f) {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) f(i);
 }
-static bool map_pdl() {   // ECFFT_B200_PDL (default 1), the knob of sym_kernel.cu
+// ECFFT_B200_MAP_PDL=1: programmatic dependent launch for the glue kernels too.  Off by default: measured mixed
+// (profiles/r02_ac_glue_pdl.txt, together with k_extend_sym's: ENTER -> EXIT at 2^12 1.95 -> 1.80 ms, DEGREE 2^16 1.32 -> 1.17 ms,
+// but VANISH 2^16 0.84 -> 1.14 ms).
+static bool map_pdl() {
   static int v = -1;
   if (v < 0) {
-    const char* e = getenv("ECFFT_B200_PDL");
-    v = e ? (atoi(e) != 0) : 1;
+    const char* e = getenv("ECFFT_B200_MAP_PDL");
+    v = e ? (atoi(e) != 0) : 0;
   }
   return v != 0;
 }
@@ -104,9 +107,6 @@ static void map(size_t n, cudaStream_t st, F f) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  // on every launch, like k_extend_sym's (ENTER -> EXIT at 2^12: 1.88 -> 1.79 ms, EXIT 2^22 30.84 -> 30.52 ms,
-  // profiles/r02_z_ab_pdl.txt).  Attaching it to some launches of a stream and not to others measured worst on the m31
-  // kernels (m31.cu pdl_mode), so there is no per-grid rule here.
   cfg.numAttrs = map_pdl() ? 1 : 0;
   ECFFT_CUDA(cudaLaunchKernelEx(&cfg, k_map<F>, n, f));
   prof::count_launch();

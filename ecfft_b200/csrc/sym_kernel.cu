@@ -612,15 +612,23 @@ bool flow_enabled() {
   return v != 0;
 }
 
-static bool pdl_enabled() {
+// Programmatic dependent launch, by grid size (ECFFT_B200_PDL: 0 = never, 1 = this rule (default), 2 = always).
+// Measured per size on one box (profiles/r02_ae_ab_pdl_tma_streams.txt, r02_ad_*): launches of up to ~64 tiles gain
+// (ENTER 2^16 0.660 -> 0.613 ms, EXIT 2^16 2.81 -> 2.62 ms, ENTER -> EXIT 2^12 8 %); launches of 128-1024 tiles LOSE,
+// badly where the grid is a fraction of one wave (EXIT 2^18 3.91 -> 6.72 ms, EXIT 2^19 5.35 -> 7.72 ms, ENTER 2^18
+// 1.13 -> 1.58 ms, ENTER 2^19 on four streams 1.77 -> 2.10 ms): the dependent grid's CTAs are placed while the running
+// grid still holds its slots, so an under-filled grid ends up packed on few SMs instead of spread over all 148;
+// multi-wave launches are neutral to +1 % (ENTER 2^22 14.19 -> 14.17 ms, EXIT 2^22 30.95 -> 30.57 ms).
+static int pdl_mode() {
   static int v = -1;
   if (v < 0) {
-    // on by default: 6 % at n = 2^16, 3 % at 2^19, neutral at 2^22 (profiles/r02_g_pdl.txt)
     const char* e = getenv("ECFFT_B200_PDL");
-    v = e ? (atoi(e) != 0) : 1;
+    v = e ? atoi(e) : 1;
+    if (v < 0 || v > 2) v = 1;
   }
-  return v != 0;
+  return v;
 }
+static bool pdl_for(size_t tiles) { return pdl_mode() == 2 || (pdl_mode() == 1 && (tiles <= 64 || tiles >= 2048)); }
 // ECFFT_B200_TMA (default 1): tile loads as cp.async.bulk.tensor copies completing on an mbarrier; 0 = cp.async.
 // Measured on one B200, same box, bit-identical results (profiles/r02_m_ab_tma.txt): ENTER 2^22 14.27 -> 13.95 ms,
 // 2^19 2.097 -> 2.070 ms, EXTEND 2^20 0.356 -> 0.350 ms, EXIT 2^22 31.19 -> 31.08 ms (its strided-view passes keep cp.async).
@@ -686,7 +694,7 @@ static void launch_kernel(void (*kern)(Args...), size_t tiles, int nt, size_t sm
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = pdl_for(tiles) ? 1 : 0;
   ECFFT_CUDA(cudaLaunchKernelEx(&cfg, kern, args...));
 }
 template <int NT, int MINB>
