@@ -180,10 +180,12 @@ void enter_peer(const Engine& eng, const Fp* chunk, size_t n, int rank, int worl
   PeerCtx ctx{st, rank, world, bases, epoch, c, peer_timeout_ms()};
   ctx.begin();
   size_t sA = ctx.new_slot();
-  // Streams for the rank-local ENTER, measured on 2 / 4 / 8 B200s at n = 2^22 (profiles/r02_y_*): chunks of 2^20 elements
-  // and more gain from two streams (7.73 vs 8.08 ms at 2 GPUs, 4.59 vs 4.72 ms at 4), chunks of 2^19 lose with any fork
-  // (3.18 ms on one stream, 3.44 on two, 3.50 on four at 8 GPUs): the flag waits that follow expose the join
-  eng.enter_range(chunk, ctx.slot(rank, sA), c, 1, c, c >= ((size_t)1 << 20) ? 2 : 1);
+  // Streams for the rank-local ENTER, measured on 2 / 4 / 8 B200s at n = 2^22 (profiles/r02_y_*, r02_ag_*): chunks of 2^20
+  // elements and more run best on two streams (7.73 vs 8.08 ms on one at 2 GPUs, 4.59 vs 4.72 / 4.68 ms on one / four at 4),
+  // chunks of 2^19 on the automatic four (8 GPUs: 3.12 ms, 3.13 on two, 3.27 on one).  (Before programmatic dependent
+  // launch was restricted by grid size the order at 8 GPUs was the reverse — 3.18 / 3.44 / 3.50 ms — for the reason given
+  // at pdl_mode in sym_kernel.cu.)
+  eng.enter_range(chunk, ctx.slot(rank, sA), c, 1, c, c >= ((size_t)1 << 20) ? 2 : 0);
   int r = 1;
   for (size_t m = 2 * c; m <= n; m *= 2, r *= 2) {
     const Level& lv = eng.level_for(m);
