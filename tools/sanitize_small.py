@@ -22,5 +22,15 @@ ok = ok and (g.redc_z0(ev, xnn) == c.redc_z0(ev, xnn)).all()
 ok = ok and (g.modular_reduce(ev, xnn, c.table("z0z0_rem_xnn_s")) == c.modular_reduce(ev, xnn, c.table("z0z0_rem_xnn_s"))).all()
 ok = ok and (g.vanish(x[: n // 2]) == c.vanish(x[: n // 2])).all()
 ok = ok and g.degree(ev) == c.degree(ev)
+# round 2: the batched host call, a cut of ENTER's depth range (folded combines), the second field
+xs = np.stack([O.random_elements(1 << 11, seed=20 + i) for i in range(3)])
+ys = g.enter_many(xs)
+ok = ok and all((ys[i] == c.enter(xs[i])).all() for i in range(3))
+from oracle import m31_ref
+g31, c31 = ecfft_b200.m31.build_fftree(1 << 9), m31_ref.FFTree.build(1 << 9)
+v = [(i * 2654435761) % m31_ref.P for i in range(1 << 9)]
+e31 = g31.enter(np.asarray(v, dtype=np.uint32))
+ok = ok and e31.tolist() == c31.enter(v) and g31.exit(e31).tolist() == v
+ok = ok and g31.degree(e31) == c31.degree(c31.enter(v)) and g31.vanish(np.asarray(v[:128], dtype=np.uint32)).tolist() == c31.vanish(v[:128])
 print("sanitize run parity", "OK" if ok else "FAIL")
 sys.exit(0 if ok else 1)
