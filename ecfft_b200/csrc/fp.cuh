@@ -277,6 +277,9 @@ FP_HD Fp fp_sub_lazy2(const Fp& a, const Fp& b) {
 // Short forms of fp_add_lazy / fp_sub_lazy2 for the butterfly kernels: the DELTA correction is applied
 // to the low two limbs only and the (probability ~2^-31) carry/borrow out of them takes a branch.
 FP_HD Fp fp_add_lazy_f(const Fp& a, const Fp& b) {
+#ifdef FP_BRANCHFREE_ADDSUB   // A/B switch: the straight-line forms (more instructions, no basic-block boundary inside a butterfly)
+  return fp_add_lazy(a, b);
+#endif
   Fp s;
   s.v[0] = add_cc(a.v[0], b.v[0]);
 #pragma unroll
@@ -297,6 +300,9 @@ FP_HD Fp fp_add_lazy_f(const Fp& a, const Fp& b) {
   return s;
 }
 FP_HD Fp fp_sub_lazy2_f(const Fp& a, const Fp& b) {
+#ifdef FP_BRANCHFREE_ADDSUB
+  return fp_sub_lazy2(a, b);
+#endif
   Fp d;
   d.v[0] = sub_cc(a.v[0], b.v[0]);
 #pragma unroll
@@ -394,8 +400,11 @@ FP_HD Fp fp_reduce(const MulAcc& A) {
   for (int k = 2; k < 16; k++) t[k] = addc_cc(A.e[k], A.o[k - 1]);
   t[16] = addc(A.e[16], 0u);
 
-#ifndef FP_REDUCE_ALIGNED   // default: three carry chains on one array — measured 5% faster in the tile kernel
-                          // than the move-free even/odd-aligned form below (profiles/r01_g_ab_variants.txt)
+#ifdef FP_REDUCE_CHAINED   // the round-1 default: three carry chains on one array — 5 % faster in the radix-2 tile kernel
+                          // (profiles/r01_g_ab_variants.txt), 2 % SLOWER in k_extend_sym than the form below, whose chains
+                          // never change register-pair alignment: ptxas places the moves the chained form needs on the
+                          // multiplier's own pipe as IMAD.MOV (655 -> 369 moves per kernel; ENTER 2^22 14.13 -> 13.84 ms,
+                          // EXIT 2^22 30.59 -> 30.04 ms, profiles/r02_aj_ab_arith_variants.txt)
   // r = lo + 977*hi + (hi << 32), hi = t[8..16]  (r < 2^291 -> 10 limbs): three chains on one array
   uint32_t r[10];
   r[0] = mad_lo_cc(t[8], FP_C977, t[0]);
