@@ -16,3 +16,4 @@ timeout 900 ncu --set full --clock-control none --import-source on --profile-fro
 python tools/ncu_summary.py full gpurun_out/r02_${S}_ncu_full_extend_sym.ncu-rep > gpurun_out/r02_${S}_ncu_full_extend_sym.txt 2>&1; head -30 gpurun_out/r02_${S}_ncu_full_extend_sym.txt | cut -c1-200
 python tools/bench_configs.py 22 2>&1 | tee gpurun_out/r02_${S}_bench_configs.jsonl | cut -c1-160
 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r02_${S}_bench_reference.json 2>/dev/null; cut -c1-500 gpurun_out/r02_${S}_bench_reference.json
+python tools/ab_variants.py enter 22 20 '' 'ECFFT_B200_SYM_VARIANT=0' 2>&1 | tee gpurun_out/r02_${S}_ab_shape_final.txt
