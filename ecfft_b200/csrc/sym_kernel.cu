@@ -596,6 +596,18 @@ static int sym_variant() {
   }
   return v;
 }
+// ECFFT_B200_SYM_AUTO (default 1): launches of 2048 tiles and more take shape 0 (five CTAs of 96 registers per SM), smaller
+// ones the default shape 1 — measured after the aligned reduction freed registers (profiles/r02_ak_ab_auto_shape.txt,
+// r02_p_ab_shape_final.txt): ENTER 2^22 13.84 -> 13.69 ms, EXIT 2^22 30.02 -> 29.96 ms, while at 2^19 shape 0 loses
+// (1.73 -> 1.80 ms), so the grid decides.
+static bool sym_auto_shape() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ECFFT_B200_SYM_AUTO");
+    v = e ? (atoi(e) != 0) : 1;
+  }
+  return v != 0;
+}
 static uint32_t sym_log_tile() { return sym_variant() == 3 ? 11 : sym_variant() == 4 ? 9 : 10; }
 uint32_t flow_log_tile() { return sym_log_tile(); }
 bool flow_enabled() {
@@ -736,7 +748,11 @@ static void launch_sym(const SymParams& p_in, cudaStream_t st) {
   if (tiles > 0x7fffffffull) throw Error(ERR_INVALID_ARG, "extend: grid too large");
   const bool timed = prof::enabled();
   if (timed) prof::record_begin(prof::EXTEND_TILE, pass_alg_bytes(p), st);
-  switch (sym_variant()) {
+  // Shapes 0 and 1 run the same 1024-element tile with 128 threads, so the choice is made per launch (sym_auto_shape):
+  // five CTAs of 96 registers per SM for multi-wave grids, four of 122 registers otherwise.
+  int shape = sym_variant();
+  if (shape == 1 && sym_auto_shape() && tiles >= 2048) shape = 0;
+  switch (shape) {
     case 1: launch_shape<128, 4>(p, tiles, st); break;
     case 2: launch_shape<256, 3>(p, tiles, st); break;
     case 3: launch_shape<256, 2>(p, tiles, st); break;
