@@ -129,6 +129,107 @@ def test_chain_constants():
     assert M.two_adicity(M.SUBGROUP_GENERATOR, M.CURVE_A, M.CURVE_B) == M.SUBGROUP_TWO_ADICITY
 
 
+# ---- golden vectors from the real crate, when a maintainer has produced them (tools/rust_golden) ------------------------
+import os
+
+_GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+GOLDEN = os.environ.get("ECFFT_ARKWORKS_M31_GOLDEN") or os.path.join(_GOLDEN_DIR, "arkworks_m31_n64.txt")
+if not os.path.exists(GOLDEN):   # tools/rust_golden prints both fields to one stream: its whole output may sit in arkworks_n64.txt
+    _both = os.path.join(_GOLDEN_DIR, "arkworks_n64.txt")
+    if os.path.exists(_both) and "vec32 m31." in open(_both).read():
+        GOLDEN = _both
+
+
+def parse_golden(path):
+    out = {}
+    with open(path) as f:
+        for line in f:
+            parts = line.split()
+            if len(parts) >= 2 and parts[0] == "vec32" and parts[1].startswith("m31."):
+                raw = bytes.fromhex(parts[2]) if len(parts) > 2 else b""
+                out[parts[1][4:]] = np.frombuffer(raw, dtype="<u4").astype(np.uint32).tolist()
+            elif len(parts) == 3 and parts[0] == "num" and parts[1].startswith("m31."):
+                out[parts[1][4:]] = int(parts[2])
+    return out
+
+
+def check_against_golden(tree, g):
+    """every vector of the file against an FFTree-like object (the restatement, or the CUDA path through lists)"""
+    n = len(g["enter.in"])
+    assert tree.eval_domain() == g["leaves"]
+    assert tree.enter(g["enter.in"]) == g["enter.out"]
+    assert tree.exit(g["exit.in"]) == g["exit.out"]
+    assert tree.extend(g["extend.in"], 1) == g["extend_s1.out"]
+    assert tree.extend(g["extend.in"], 0) == g["extend_s0.out"]
+    assert tree.mextend(g["extend.in"], 1) == g["mextend_s1.out"]
+    assert tree.redc_z0(g["exit.in"], g["xnn_s"]) == g["redc_z0.out"]
+    assert tree.modular_reduce(g["exit.in"], g["xnn_s"], g["z0z0_rem_xnn_s"]) == g["mod.out"]
+    assert tree.vanish(g["extend.in"]) == g["vanish.out"]
+    assert tree.degree(g["enter.out"]) == g["degree.out"]
+    assert n == 64
+
+
+def write_golden_from_restatement(path):
+    rng = random.Random(11)
+    t = M.FFTree.build(64)
+    vec = {"leaves": t.eval_domain(), "xnn_s": t.xnn_s, "z0z0_rem_xnn_s": t.z0z0}
+    vec["enter.in"] = [rng.randrange(P) for _ in range(64)]
+    vec["enter.out"] = t.enter(vec["enter.in"])
+    vec["exit.in"] = [rng.randrange(P) for _ in range(64)]
+    vec["exit.out"] = t.exit(vec["exit.in"])
+    vec["extend.in"] = [rng.randrange(P) for _ in range(32)]
+    vec["extend_s1.out"], vec["extend_s0.out"] = t.extend(vec["extend.in"], 1), t.extend(vec["extend.in"], 0)
+    vec["mextend_s1.out"] = t.mextend(vec["extend.in"], 1)
+    vec["redc_z0.out"] = t.redc_z0(vec["exit.in"], t.xnn_s)
+    vec["mod.out"] = t.modular_reduce(vec["exit.in"], t.xnn_s, t.z0z0)
+    vec["vanish.out"] = t.vanish(vec["extend.in"])
+    with open(path, "w") as f:
+        for k, v in vec.items():
+            f.write(f"vec32 m31.{k} {np.asarray(v, dtype='<u4').tobytes().hex()}\n")
+        f.write(f"num m31.degree.out {t.degree(vec['enter.out'])}\n")
+
+
+def test_golden_consumer_on_a_file_written_by_the_restatement(tmp_path):
+    """exercises the parser and the comparison (the file format of tools/rust_golden's m31 section)"""
+    path = str(tmp_path / "m31.txt")
+    write_golden_from_restatement(path)
+    check_against_golden(M.FFTree.build(64), parse_golden(path))
+
+
+@pytest.mark.skipif(not os.path.exists(GOLDEN), reason="no arkworks m31 golden file (tools/rust_golden needs cargo; not available in this image)")
+def test_restatement_against_arkworks_golden():
+    check_against_golden(M.FFTree.build(64), parse_golden(GOLDEN))
+
+
+class _GpuAsLists:
+    """the CUDA tree behind the list-based interface check_against_golden uses"""
+    def __init__(self, t):
+        self.t = t
+
+    def eval_domain(self):
+        return self.t.eval_domain(64).tolist()
+
+    def __getattr__(self, name):
+        fn = getattr(self.t, name)
+
+        def call(*args):
+            conv = [np.asarray(a, dtype=np.uint32) if isinstance(a, list) else a for a in args]
+            r = fn(*conv)
+            return r.tolist() if hasattr(r, "tolist") else r
+        return call
+
+
+@pytest.mark.gpu
+def test_cuda_path_against_golden_file(tmp_path):
+    """the CUDA path against the arkworks file when present, else against the file the restatement writes"""
+    import ecfft_b200
+    path = GOLDEN
+    if not os.path.exists(path):
+        path = str(tmp_path / "m31.txt")
+        write_golden_from_restatement(path)
+    check_against_golden(_GpuAsLists(ecfft_b200.m31.build_fftree(64)), parse_golden(path))
+
+
 # ---- GPU ------------------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def trees():

@@ -35,7 +35,44 @@ fn vec_line(name: &str, v: &[Fp]) {
     println!("vec {} {}", name, limbs(v));
 }
 
+/// The same for the second field (src/lib.rs:190-215): `vec32 m31.<name> <hex>`, 4 bytes per element = the u32 that
+/// `ark_ff_optimized::fp31::Fp(pub u32)` holds.  tests/test_m31.py reads these lines from tests/golden/arkworks_n64.txt (this
+/// program's whole output) or from tests/golden/arkworks_m31_n64.txt.
+fn m31_vectors() {
+    use ecfft::m31::Fp as F31;
+    let n = 64usize;
+    let fftree = F31::build_fftree(n).unwrap();
+    let mut rng = StdRng::from_seed([1; 32]);
+    let v32 = |name: &str, v: &[F31]| {
+        let mut out = Vec::with_capacity(v.len() * 4);
+        for x in v {
+            out.extend_from_slice(&x.0.to_le_bytes());
+        }
+        println!("vec32 m31.{} {}", name, hex(&out));
+    };
+    v32("leaves", &fftree.subtree_with_size(n).eval_domain());
+    v32("xnn_s", &fftree.xnn_s);
+    v32("z0z0_rem_xnn_s", &fftree.z0z0_rem_xnn_s);
+    let coeffs: Vec<F31> = (0..n).map(|_| F31::rand(&mut rng)).collect();
+    let evals = fftree.enter(&coeffs);
+    v32("enter.in", &coeffs);
+    v32("enter.out", &evals);
+    let arbitrary: Vec<F31> = (0..n).map(|_| F31::rand(&mut rng)).collect();
+    v32("exit.in", &arbitrary);
+    v32("exit.out", &fftree.exit(&arbitrary));
+    let half: Vec<F31> = (0..n / 2).map(|_| F31::rand(&mut rng)).collect();
+    v32("extend.in", &half);
+    v32("extend_s1.out", &fftree.extend(&half, Moiety::S1));
+    v32("extend_s0.out", &fftree.extend(&half, Moiety::S0));
+    v32("mextend_s1.out", &fftree.mextend(&half, Moiety::S1));
+    v32("redc_z0.out", &fftree.redc_z0(&arbitrary, &fftree.xnn_s));
+    v32("mod.out", &fftree.modular_reduce(&arbitrary, &fftree.xnn_s, &fftree.z0z0_rem_xnn_s));
+    v32("vanish.out", &fftree.vanish(&half));
+    println!("num m31.degree.out {}", fftree.degree(&evals));
+}
+
 fn main() {
+    m31_vectors();
     let n = 64usize;
     let fftree = Fp::build_fftree(n).unwrap();
     let mut rng = StdRng::from_seed([1; 32]);
