@@ -282,6 +282,7 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
       const uint32_t krb = lc > 8 ? 0u : kr;                          //  so a row wider than a box goes row by row)
       const uint32_t nchunk = 1u << (lc - bc_log), nrow = 1u << (kr - krb), npair = p.pair ? 2u : 1u;
       const int c1 = (int)(gbase & ((1ull << rs) - 1)), c2 = (int)(gbase >> rs);
+      const int prow = p.pair ? (int)(1u << (p.log_h - rs)) : 0;     // rows from the u-vector's tile to the v-vector's
       if (p.tma_fence) asm volatile("fence.proxy.async;" ::: "memory");   // debugging aid (ECFFT_B200_TMA=2)
       mbar_expect_tx(mbar, T * (uint32_t)sizeof(Fp));
       for (uint32_t hf = 0; hf < 2; hf++)
@@ -289,7 +290,7 @@ __device__ __forceinline__ void sym_tile(const SymParams& p, uint4* smem_raw, un
           for (uint32_t rw = 0; rw < nrow; rw++)
             for (uint32_t cc = 0; cc < nchunk; cc++)
               tma_load_3d(&s.s[hf * T + (pb << (kr + lc)) + (rw << lc) + (cc << bc_log)], tmap, (int)(hf * 4), c1 + (int)(cc << bc_log),
-                          c2 + (int)(pb << (p.log_h - rs)) + (int)rw, mbar);
+                          c2 + (int)pb * prow + (int)rw, mbar);
     }
     if (p.pf) prefetch_stage<NT>(p, tm, cur, T, p.pre != nullptr);
     mbar_wait(mbar, 0);

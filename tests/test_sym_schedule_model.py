@@ -178,3 +178,76 @@ def test_schedule_model_matches_the_level_by_level_network():
           if r: assert mem['dst']==want,("comb",LT,log_h,nvec); ok+=1
           else: assert log_h==LT,("comb refused",LT,log_h,nvec)
   assert ok > 300
+
+
+def test_tma_box_schedule_covers_every_tile_element_once():
+    """The TMA tile load of sym_tile<.., TMA = true> (one thread issues cp.async.bulk.tensor.3d boxes of {4 limbs,
+    2^min(log_c, 8) columns, 2^krows rows — one row when a row is wider than a box}; the tensor is
+    [element >> rs][element & (2^rs - 1)][8 limbs]) must put the low / high half of every tile element exactly where the
+    cp.async loop puts it: shared-memory slot e <- global element gbase + goff(e) of TileMap.  Index arithmetic only, for
+    every pass geometry the planner produces at the real tile size (packed, strided and pair tiles, log_h up to 22)."""
+    global kernel
+    passes = []
+    saved = kernel
+    kernel = lambda p, mem: passes.append(dict(p))
+    try:
+        LT = 10
+        for log_h in range(1, 23):
+            for nvec, comb in ((1, None), (2, None), (2, dict(A='in', out='dst')), (8, dict(A='in', out='dst'))):
+                if (nvec << log_h) < 1024:
+                    continue
+                extend_sym({}, 'in', 'out', log_h, nvec, 'pre', 'post', comb, LT)
+    finally:
+        kernel = saved
+    assert len(passes) > 150
+    seen_shapes = set()
+    for p in passes:
+        T = 1 << p['log_t']
+        if p['log_t'] < 9 or p['total'] % T:
+            continue                                       # make_tile_map refuses: cp.async path
+        rs = p['log_t'] if p['packed'] else p['row_shift']
+        lc = p['log_t'] if p['packed'] else p['log_c']
+        kr = 0 if p['packed'] else p['krows']
+        assert p['total'] % (1 << rs) == 0
+        bc_log = min(lc, 8)
+        krb = 0 if lc > 8 else kr
+        seen_shapes.add((p['packed'], p['pair'], lc, kr))
+        tiles = p['total'] >> p['log_t']
+        for blk in sorted({0, 1, tiles // 2, tiles - 1}):
+            if blk >= tiles:
+                continue
+            if p['packed']:
+                tm = dict(log_c=p['log_t'], cmask=T - 1, rmask=0, krows=0, row_shift=0, log_h=p['log_h'])
+                gbase = blk << p['log_t']
+            else:
+                w, tile = blk % p['nv'], blk // p['nv']
+                ncg = p['row_shift'] - p['log_c']
+                pos0 = ((tile >> ncg) << p['lvl_hi']) + ((tile & ((1 << ncg) - 1)) << p['log_c'])
+                tm = dict(log_c=p['log_c'], cmask=(1 << p['log_c']) - 1, rmask=(1 << p['krows']) - 1, krows=p['krows'],
+                          row_shift=p['row_shift'], log_h=p['log_h'])
+                gbase = ((2 * w if p['pair'] else w) << p['log_h']) + pos0
+            want = []
+            for e in range(T):
+                rr, c = e >> tm['log_c'], e & tm['cmask']
+                want.append(gbase + ((rr >> tm['krows']) << tm['log_h']) + ((rr & tm['rmask']) << tm['row_shift']) + c)
+            got = [[None] * T, [None] * T]
+            c1, c2 = gbase & ((1 << rs) - 1), gbase >> rs
+            nchunk, nrow, npair = 1 << (lc - bc_log), 1 << (kr - krb), 2 if p['pair'] else 1
+            nbytes = 0
+            for hf in range(2):
+                for pb in range(npair):
+                    for rw in range(nrow):
+                        for cc in range(nchunk):
+                            dst = (pb << (kr + lc)) + (rw << lc) + (cc << bc_log)          # element offset inside this half
+                            prow = (1 << (p['log_h'] - rs)) if p['pair'] else 0
+                            x1, x2 = c1 + (cc << bc_log), c2 + pb * prow + rw
+                            for r in range(1 << krb):                                      # dense box: rows of 2^bc_log columns
+                                for c in range(1 << bc_log):
+                                    slot = dst + (r << bc_log) + c
+                                    assert got[hf][slot] is None, ("written twice", p, blk, slot)
+                                    got[hf][slot] = ((x2 + r) << rs) + x1 + c
+                                    nbytes += 16
+            assert got[0] == want and got[1] == want, (p, blk)
+            assert nbytes == T * 32                                                        # the mbarrier's expected byte count
+    assert any(lc > 8 and kr > 0 for _, _, lc, kr in seen_shapes)      # the shape whose rows are wider than a box
+    assert any(pair for _, pair, _, _ in seen_shapes)
